@@ -1,0 +1,175 @@
+/* stk.h -- C ABI of libstk.so, the sm_100a device side of the space-time
+ * Kronecker solve path (B200-native replacement for the NumPy/SciPy/PETSc/MPI
+ * arithmetic behind /root/reference/source/{mpi_vector,mpi_kron,wavelets,
+ * multigrid,linalg}.py).
+ *
+ * The reference has no FFI of its own (it is pure Python), so
+ * every entry point below names the reference Python call site whose
+ * arithmetic it replaces.  INTEGRATION.md shows the ctypes stubs a reference
+ * maintainer would add.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; `stream` is a cudaStream_t passed as void*
+ *    (NULL = legacy default stream).  All work is enqueued on that stream;
+ *    nothing synchronises except the *_host entry points and stk_sync.
+ *  - every function returns 0 on success or a non-zero cudaError_t / negative
+ *    argument error; stk_last_error() returns the message of the last failure
+ *    in this thread.  No exception crosses the ABI.
+ *  - the library owns no device memory except inside stk_mg handles' small
+ *    host-side descriptors; the caller allocates and frees every buffer.
+ *
+ * Data layout in HBM ("slab block"): the local part of a space-time vector,
+ * n_t local time slices x M space dofs, is stored TIME-FASTEST:
+ *      x[i * ld + t],  i in [0,M), t in [0,n_t),  ld = n_t rounded up to 4,
+ * with the pad entries t in [n_t, ld) kept equal to zero by every kernel.
+ * A CSR nonzero a_ij of a space operator therefore multiplies a contiguous run
+ * of time values (coalesced, matrix read once per row for all slices), and a
+ * time operator is a unit-stride stencil; no transpose is ever needed.
+ * The reference's X_loc (n_t, M) row-major array is the transpose of this
+ * block (stk_block_from_rowmajor / stk_block_to_rowmajor convert).
+ */
+#ifndef STK_H
+#define STK_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STK_VERSION 100
+
+int stk_version(void);
+const char *stk_last_error(void);
+/* cudaStreamSynchronize(stream). */
+int stk_sync(void *stream);
+/* Number of kernels this library has launched in this process (bench.py's
+ * gpu_launches). */
+int64_t stk_launch_count(void);
+
+/* ---- layout conversion / host boundary ---------------------------------
+ * mpi_vector.py:62-71 (X_loc storage), :124-138 (scatter/gather). */
+/* dst block (M, ld) <- src (n_t, M) row-major, both on the device. */
+int stk_block_from_rowmajor(const double *src, int n_t, int M, double *dst,
+                            int ld, void *stream);
+/* dst (n_t, M) row-major <- src block (M, ld), both on the device. */
+int stk_block_to_rowmajor(const double *src, int ld, int n_t, int M,
+                          double *dst, void *stream);
+/* Host entry points (HOST pointers in the reference's X_loc layout; the copy
+ * and the transpose happen inside, `staging` is a device scratch buffer of
+ * n_t*M doubles).  They synchronise the stream before returning. */
+int stk_block_upload_host(const double *host_rowmajor, int n_t, int M,
+                          double *dst, int ld, double *staging, void *stream);
+int stk_block_download_host(const double *src, int ld, int n_t, int M,
+                            double *host_rowmajor, double *staging,
+                            void *stream);
+
+/* ---- BLAS-1 on blocks (n = M*ld doubles, pads are zero) -----------------
+ * mpi_vector.py:84-122 (in-place ops), linalg.py:29-30,39-40. */
+int stk_axpy(double a, const double *x, double *y, int64_t n, void *stream);
+int stk_scale(double a, double *x, int64_t n, void *stream);
+/* y = x + a*y   (linalg.py:39-40: p *= beta; p += z). */
+int stk_xpay(const double *x, double a, double *y, int64_t n, void *stream);
+/* w += a*p ; r -= a*t  in one pass (linalg.py:29-30). */
+int stk_pcg_update(double a, const double *p, const double *t, double *w,
+                   double *r, int64_t n, void *stream);
+/* out_dev[0] = sum_k x[k]*y[k], single pass, deterministic: per-CTA
+ * warp-shuffle partials, the last CTA adds them in index order
+ * (mpi_vector.py:205-210 local np.dot; the allreduce is the caller's).
+ * `ws` is a device workspace of STK_DOT_WS doubles, zero-initialised once. */
+#define STK_DOT_WS 2048
+int stk_dot(const double *x, const double *y, int64_t n, double *ws,
+            double *out_dev, void *stream);
+
+/* ---- space operator: batched CSR SpMM over all time slices --------------
+ * mpi_kron.py:143-150 (IdentityKronMatMPI), linop.py:75-79, and the CSR
+ * products inside multigrid.py:174,180.
+ *   y[i,t] = alpha * sum_k coef_k[t] * sum_p vals_k[p] * x[indices[p], t]
+ *            + beta * z[i,t]
+ * K = 1: coef ignored (may be NULL), plain CSR.  K = 2: the matrix of slice t
+ * is coef0[t]*vals0 + coef1[t]*vals1 on a shared sparsity pattern (e.g.
+ * 2^j M_x + alpha A_x, heateq_mpi.py:97-98); coef arrays have ld entries.
+ * z may be NULL when beta == 0 and may alias y; x must not alias y. */
+int stk_space_spmm(int nrows, const int *indptr, const int *indices, int K,
+                   const double *vals0, const double *vals1,
+                   const double *coef0, const double *coef1, const double *x,
+                   double alpha, double beta, const double *z, double *y,
+                   int ld, void *stream);
+
+/* ---- time operator: sparse matrix along the time axis -------------------
+ * mpi_kron.py:186-201 (TridiagKronIdentityMPI), :285-317
+ * (SparseKronIdentityMPI), :240-256 (MatKronIdentityMPI after permute).
+ *   y[i,t] = alpha * sum_p vals[p] * X(i, indices[p]) + beta * y[i,t],
+ *   t in [0, nrows_t); pads t in [nrows_t, ldy) are written as zero when
+ *   beta == 0.
+ * X(i,c) = x[i*ldx + c] for c < ncols_local, else the halo slice
+ * xh[(c-ncols_local)*M + i] (slice-major, as received from a neighbour rank,
+ * mpi_vector.py:140-203).  y must not alias x. */
+int stk_time_apply(int M, int nrows_t, const int *indptr, const int *indices,
+                   const double *vals, const double *x, int ldx,
+                   int ncols_local, const double *xh, double alpha,
+                   double beta, double *y, int ldy, void *stream);
+/* out[h*M + i] = x[i*ld + tidx[h]]   (pack time slices for a send). */
+int stk_pack_slices(const double *x, int ld, int M, const int *tidx, int n,
+                    double *out, void *stream);
+/* x[i*ld + tidx[h]] = beta * x[...] + alpha * in[h*M + i]. */
+int stk_unpack_slices(double *x, int ld, int M, const int *tidx, int n,
+                      const double *in, double alpha, double beta,
+                      void *stream);
+
+/* ---- wavelet transform in time, in-place lifting ------------------------
+ * wavelets.py:106-134 (WaveletTransformOp._matmat/_rmatmat, interleaved
+ * ordering) for a block holding the whole time axis (n_t = 2^J + 1).
+ * transpose = 0: x <- W x (levels 1..J); transpose = 1: x <- W^T x. */
+int stk_wavelet_lift(int M, int J, int transpose, double *x, int ld,
+                     void *stream);
+
+/* ---- multigrid V-cycle, batched over all time slices --------------------
+ * multigrid.py:130-197 (MultiGrid), :100-127 (PETSc MatSOR sweeps).
+ * A handle describes one Galerkin hierarchy (levels 0..nlevels-1, the last
+ * one finest) by device pointers the caller keeps alive. */
+typedef struct stk_mg stk_mg;
+stk_mg *stk_mg_create(int nlevels, int smoothsteps, int vcycles, int K);
+void stk_mg_destroy(stk_mg *mg);
+/* Level matrix (union pattern, K value arrays, K diagonals) and its
+ * Gauss-Seidel schedule: sched_rows (device) lists the rows wavefront by
+ * wavefront, phase_ptr (HOST, nphases+1 entries) delimits the wavefronts.
+ * Rows inside a wavefront are mutually independent and every row comes after
+ * all its lower-numbered neighbours, so running the wavefronts in order is
+ * exactly the lexicographic sweep of multigrid.py:89-97 / MatSOR. */
+int stk_mg_set_level(stk_mg *mg, int level, int nrows, const int *indptr,
+                     const int *indices, const double *vals0,
+                     const double *vals1, const double *diag0,
+                     const double *diag1, const int *sched_rows,
+                     const int *phase_ptr_host, int nphases);
+/* Prolongation level-1 -> level (CSR, nrows(level) x nrows(level-1)) and its
+ * transpose (multigrid.py:39-60). */
+int stk_mg_set_transfer(stk_mg *mg, int level, const int *p_indptr,
+                        const int *p_indices, const double *p_vals,
+                        const int *r_indptr, const int *r_indices,
+                        const double *r_vals);
+/* Doubles of workspace stk_mg_apply needs for blocks of pitch ld. */
+int64_t stk_mg_workspace(const stk_mg *mg, int ld);
+/* x <- `vcycles` V(nu,nu)-cycles for A(t) x = b from x = 0, every slice t of
+ * the block at once.  coef0/coef1: per-slice coefficients (K = 2) or NULL.
+ * coarse_inv: G dense inverses (n0 x n0, row-major) of the coarsest matrix;
+ * coarse_group[t] selects the one of slice t (NULL: group 0 for all). */
+int stk_mg_apply(stk_mg *mg, const double *coef0, const double *coef1,
+                 const double *coarse_inv, const int *coarse_group,
+                 const double *b, double *x, int ld, double *ws,
+                 void *stream);
+/* One family of Gauss-Seidel sweeps on a level (exposed for tests):
+ * `nsweeps` forward (backward = 0) or backward sweeps of u on level. */
+int stk_mg_smooth(stk_mg *mg, int level, int nsweeps, int backward,
+                  const double *coef0, const double *coef1, const double *f,
+                  double *u, int ld, void *stream);
+
+/* HOST helper (host pointers): wave[i] = wavefront of row i in the
+ * lexicographic Gauss-Seidel dependency DAG of a symmetric-pattern CSR matrix
+ * (0 for rows without lower-numbered neighbours).  Returns the number of
+ * wavefronts.  Setup only; replaces nothing in the reference (PETSc sweeps
+ * rows one by one). */
+int stk_gs_wavefronts(int n, const int *indptr, const int *indices, int *wave);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STK_H */

@@ -1,0 +1,160 @@
+"""Communicator: the role mpi4py's COMM_WORLD plays in the reference
+(SURVEY.md 2b), on top of torch.distributed -- NCCL over NVLink between the
+B200s of one box, gloo for the CPU tests of the host logic.
+
+One process per GPU.  Only the operations the hot path needs exist:
+  * `exchange`  : grouped point-to-point sends/receives of device buffers
+                  (halo slices, wavelet boundary slices;
+                  mpi_vector.py:140-203's Isend/Irecv),
+  * `all_to_all`: the time<->space transpose (mpi_vector.py:212-240),
+  * `allreduce_sum`: Krylov scalars (mpi_vector.py:209),
+  * object bcast/gather/Barrier for setup and statistics.
+"""
+import time
+
+import torch
+
+
+def Wtime():
+    return time.perf_counter()
+
+
+class SerialComm:
+    """One rank, no library underneath (python3 heateq.py-style runs)."""
+    rank, size = 0, 1
+
+    def Get_rank(self):
+        return 0
+
+    def Get_size(self):
+        return 1
+
+    def Split_type(self, *_):
+        return self
+
+    def allreduce_sum(self, t):
+        return t
+
+    def allreduce(self, obj):
+        return obj
+
+    def bcast(self, obj, root=0):
+        return obj
+
+    def gather(self, obj, root=0):
+        return [obj]
+
+    def Barrier(self):
+        pass
+
+    def exchange(self, sends, recvs):
+        # a rank never messages itself in the plans built by timeop.py
+        assert not sends and not recvs
+
+    def all_to_all(self, send_chunks, recv_chunks):
+        recv_chunks[0].copy_(send_chunks[0])
+
+
+class TorchComm:
+    """torch.distributed process group (nccl on GPUs, gloo on CPU)."""
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        assert dist.is_initialized()
+        self.dist, self.group = dist, group
+        self.rank = dist.get_rank(group)
+        self.size = dist.get_world_size(group)
+
+    def Get_rank(self):
+        return self.rank
+
+    def Get_size(self):
+        return self.size
+
+    def Split_type(self, *_):
+        return self  # one box: every rank shares the node
+
+    def allreduce_sum(self, t):
+        """In-place sum of a tensor over the ranks; returns it."""
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def allreduce(self, obj):
+        """Python-number sum (the reference's lowercase comm.allreduce)."""
+        objs = [None] * self.size
+        self.dist.all_gather_object(objs, obj, group=self.group)
+        total = objs[0]
+        for o in objs[1:]:
+            total = total + o
+        return total
+
+    def bcast(self, obj, root=0):
+        box = [obj]
+        self.dist.broadcast_object_list(box, src=root, group=self.group)
+        return box[0]
+
+    def gather(self, obj, root=0):
+        objs = [None] * self.size
+        self.dist.all_gather_object(objs, obj, group=self.group)
+        return objs if self.rank == root else None
+
+    def Barrier(self):
+        self.dist.barrier(group=self.group)
+
+    def exchange(self, sends, recvs):
+        """sends / recvs: {peer: contiguous tensor}.  All transfers are posted
+        as one batch (a single NCCL group) and waited for."""
+        ops = []
+        for peer in sorted(recvs):
+            ops.append(self.dist.P2POp(self.dist.irecv, recvs[peer], peer,
+                                       self.group))
+        for peer in sorted(sends):
+            ops.append(self.dist.P2POp(self.dist.isend, sends[peer], peer,
+                                       self.group))
+        if ops:
+            for req in self.dist.batch_isend_irecv(ops):
+                req.wait()
+
+    def all_to_all(self, send_chunks, recv_chunks):
+        """send_chunks[p] goes to rank p, recv_chunks[p] comes from rank p."""
+        if send_chunks[0].is_cuda:
+            self.dist.all_to_all(recv_chunks, send_chunks, group=self.group)
+        else:  # gloo has no all_to_all: post the pairwise transfers
+            me = self.rank
+            recv_chunks[me].copy_(send_chunks[me])
+            self.exchange(
+                {p: send_chunks[p] for p in range(self.size) if p != me},
+                {p: recv_chunks[p] for p in range(self.size) if p != me})
+
+
+_world = None
+
+
+def world():
+    """COMM_WORLD: the default torch.distributed group when initialised (one
+    process per GPU under torchrun), else a serial communicator."""
+    global _world
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        if not isinstance(_world, TorchComm):
+            _world = TorchComm()
+    elif _world is None or isinstance(_world, TorchComm):
+        _world = SerialComm()
+    return _world
+
+
+def init_from_env(backend=None):
+    """Initialise torch.distributed from torchrun's environment (RANK,
+    LOCAL_RANK, WORLD_SIZE, MASTER_ADDR, MASTER_PORT) and bind this process to
+    its GPU.  No-op for single-process runs."""
+    import os
+    import torch.distributed as dist
+    if int(os.environ.get('WORLD_SIZE', '1')) > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = 'nccl' if torch.cuda.is_available() else 'gloo'
+        if torch.cuda.is_available():
+            torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group(backend=backend)
+    elif torch.cuda.is_available():
+        torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
+    return world()

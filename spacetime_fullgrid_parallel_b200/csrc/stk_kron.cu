@@ -1,0 +1,190 @@
+// Kronecker applies of libstk: space CSR SpMM batched over time slices, sparse
+// time operator along the fast axis, slice pack/unpack for the halo exchange.
+// Replaces scipy's csr_matvecs at the call sites of
+// /root/reference/source/mpi_kron.py:131,149,194,199-200,250,307-315 and
+// linop.py:75-79.
+//
+// Thread mapping (both kernels): one thread owns a pair of adjacent time
+// values (a double2) of one row; consecutive threads walk the time axis first,
+// so every load of x[j, :] and every store of y[i, :] is a contiguous
+// 16-byte-per-lane access and the CSR row (indices, values) is a warp-uniform
+// broadcast load that is read once for all time slices.
+#include "stk_common.cuh"
+
+namespace stk {
+
+// y[i,t] = alpha * (A x)[i,t] + beta * z[i,t]; K=2: A(t) = c0[t] A0 + c1[t] A1.
+template <int K, bool HAS_Z>
+__global__ void __launch_bounds__(256)
+    k_space_spmm(int nrows, const int *__restrict__ indptr, const int *__restrict__ indices,
+                 const double *__restrict__ vals0, const double *__restrict__ vals1,
+                 const double *__restrict__ coef0, const double *__restrict__ coef1,
+                 const double *__restrict__ x, double alpha, double beta, const double *z,
+                 double *y, int ld, unsigned ld2) {
+    unsigned k = blockIdx.x * 256u + threadIdx.x;
+    unsigned i = k / ld2;
+    if (i >= (unsigned)nrows) return;
+    unsigned c = (k - i * ld2) * 2u;
+    int p0 = __ldg(indptr + i), p1 = __ldg(indptr + i + 1);
+    double2 s0 = make_double2(0.0, 0.0), s1 = make_double2(0.0, 0.0);
+    for (int p = p0; p < p1; ++p) {
+        int j = __ldg(indices + p);
+        double2 xv = ldv2(x + (size_t)j * ld + c);
+        double a0 = __ldg(vals0 + p);
+        s0.x = fma(a0, xv.x, s0.x);
+        s0.y = fma(a0, xv.y, s0.y);
+        if (K == 2) {
+            double a1 = __ldg(vals1 + p);
+            s1.x = fma(a1, xv.x, s1.x);
+            s1.y = fma(a1, xv.y, s1.y);
+        }
+    }
+    if (K == 2) {
+        double2 c0 = ldg2(coef0 + c), c1 = ldg2(coef1 + c);
+        s0.x = fma(c0.x, s0.x, c1.x * s1.x);
+        s0.y = fma(c0.y, s0.y, c1.y * s1.y);
+    }
+    size_t o = (size_t)i * ld + c;
+    double2 out;
+    if (HAS_Z) {
+        double2 zv = ldv2(z + o);
+        out.x = fma(alpha, s0.x, beta * zv.x);
+        out.y = fma(alpha, s0.y, beta * zv.y);
+    } else {
+        out.x = alpha * s0.x;
+        out.y = alpha * s0.y;
+    }
+    stv2(y + o, out);
+}
+
+// y[i,t] = alpha * sum_p T[t,p] X(i, col_p) + beta * y[i,t].
+// One thread per (i, t); t fastest.  X(i, c) comes from the block for local
+// columns and from the slice-major halo buffer otherwise.
+template <bool ACC>
+__global__ void __launch_bounds__(256)
+    k_time_apply(int M, int nrows_t, const int *__restrict__ indptr,
+                 const int *__restrict__ indices, const double *__restrict__ vals,
+                 const double *__restrict__ x, int ldx, int ncols_local,
+                 const double *__restrict__ xh, double alpha, double beta,
+                 double *__restrict__ y, int ldy) {
+    unsigned k = blockIdx.x * 256u + threadIdx.x;
+    unsigned i = k / (unsigned)ldy;
+    if (i >= (unsigned)M) return;
+    unsigned t = k - i * (unsigned)ldy;
+    size_t o = (size_t)i * ldy + t;
+    if (t >= (unsigned)nrows_t) {
+        if (!ACC) y[o] = 0.0;
+        return;
+    }
+    const double *xi = x + (size_t)i * ldx;
+    double s = 0.0;
+    int p1 = __ldg(indptr + t + 1);
+    for (int p = __ldg(indptr + t); p < p1; ++p) {
+        int c = __ldg(indices + p);
+        double xv = (c < ncols_local) ? xi[c] : __ldg(xh + (size_t)(c - ncols_local) * M + i);
+        s = fma(__ldg(vals + p), xv, s);
+    }
+    y[o] = ACC ? fma(alpha, s, beta * y[o]) : alpha * s;
+}
+
+__global__ void __launch_bounds__(256)
+    k_pack_slices(const double *__restrict__ x, int ld, int M, const int *__restrict__ tidx,
+                  int n, double *__restrict__ out) {
+    // threads walk i (coalesced store); the strided gather of x is a few
+    // slices per block only.
+    size_t k = (size_t)blockIdx.x * 256u + threadIdx.x;
+    if (k >= (size_t)n * M) return;
+    int h = (int)(k / M);
+    int i = (int)(k - (size_t)h * M);
+    out[k] = x[(size_t)i * ld + __ldg(tidx + h)];
+}
+
+__global__ void __launch_bounds__(256)
+    k_unpack_slices(double *__restrict__ x, int ld, int M, const int *__restrict__ tidx, int n,
+                    const double *__restrict__ in, double alpha, double beta) {
+    size_t k = (size_t)blockIdx.x * 256u + threadIdx.x;
+    if (k >= (size_t)n * M) return;
+    int h = (int)(k / M);
+    int i = (int)(k - (size_t)h * M);
+    size_t o = (size_t)i * ld + __ldg(tidx + h);
+    x[o] = (beta == 0.0) ? alpha * in[k] : fma(alpha, in[k], beta * x[o]);
+}
+
+int launch_space_spmm(int nrows, const int *indptr, const int *indices, int K,
+                      const double *vals0, const double *vals1, const double *coef0,
+                      const double *coef1, const double *x, double alpha, double beta,
+                      const double *z, double *y, int ld, cudaStream_t s) {
+    if (nrows == 0) return 0;
+    unsigned ld2 = (unsigned)ld / 2u;
+    int64_t work = (int64_t)nrows * ld2;
+    if (work >= (1ll << 32)) return fail(-2, "stk_space_spmm: block too large for 32-bit grid");
+    unsigned grid = blocks_for(work, 256);
+    bool has_z = (beta != 0.0);
+    if (has_z && z == nullptr) return fail(-1, "stk_space_spmm: beta != 0 needs z");
+#define STK_SPMM(KK, ZZ)                                                                     \
+    k_space_spmm<KK, ZZ><<<grid, 256, 0, s>>>(nrows, indptr, indices, vals0, vals1, coef0,   \
+                                              coef1, x, alpha, beta, z, y, ld, ld2)
+    if (K == 1) {
+        if (has_z) STK_SPMM(1, true); else STK_SPMM(1, false);
+    } else {
+        if (has_z) STK_SPMM(2, true); else STK_SPMM(2, false);
+    }
+#undef STK_SPMM
+    return check_launch("k_space_spmm");
+}
+
+}  // namespace stk
+
+using namespace stk;
+
+extern "C" {
+
+int stk_space_spmm(int nrows, const int *indptr, const int *indices, int K, const double *vals0,
+                   const double *vals1, const double *coef0, const double *coef1,
+                   const double *x, double alpha, double beta, const double *z, double *y, int ld,
+                   void *stream) {
+    if (K != 1 && K != 2) return fail(-1, "stk_space_spmm: K must be 1 or 2");
+    if (ld & 3) return fail(-1, "stk_space_spmm: pitch must be a multiple of 4");
+    if (K == 2 && (!vals1 || !coef0 || !coef1))
+        return fail(-1, "stk_space_spmm: K = 2 needs vals1, coef0, coef1");
+    if (x == y) return fail(-1, "stk_space_spmm: x must not alias y");
+    return launch_space_spmm(nrows, indptr, indices, K, vals0, vals1, coef0, coef1, x, alpha,
+                             beta, z, y, ld, as_stream(stream));
+}
+
+int stk_time_apply(int M, int nrows_t, const int *indptr, const int *indices,
+                   const double *vals, const double *x, int ldx, int ncols_local,
+                   const double *xh, double alpha, double beta, double *y, int ldy,
+                   void *stream) {
+    if (x == y) return fail(-1, "stk_time_apply: x must not alias y");
+    if (nrows_t > ldy) return fail(-1, "stk_time_apply: nrows_t exceeds the pitch of y");
+    if (M == 0) return 0;
+    int64_t work = (int64_t)M * ldy;
+    if (work >= (1ll << 32)) return fail(-2, "stk_time_apply: block too large");
+    unsigned grid = blocks_for(work, 256);
+    if (beta != 0.0)
+        k_time_apply<true><<<grid, 256, 0, as_stream(stream)>>>(
+            M, nrows_t, indptr, indices, vals, x, ldx, ncols_local, xh, alpha, beta, y, ldy);
+    else
+        k_time_apply<false><<<grid, 256, 0, as_stream(stream)>>>(
+            M, nrows_t, indptr, indices, vals, x, ldx, ncols_local, xh, alpha, beta, y, ldy);
+    return check_launch("k_time_apply");
+}
+
+int stk_pack_slices(const double *x, int ld, int M, const int *tidx, int n, double *out,
+                    void *stream) {
+    if (n == 0 || M == 0) return 0;
+    k_pack_slices<<<blocks_for((int64_t)n * M, 256), 256, 0, as_stream(stream)>>>(x, ld, M, tidx,
+                                                                                 n, out);
+    return check_launch("k_pack_slices");
+}
+
+int stk_unpack_slices(double *x, int ld, int M, const int *tidx, int n, const double *in,
+                      double alpha, double beta, void *stream) {
+    if (n == 0 || M == 0) return 0;
+    k_unpack_slices<<<blocks_for((int64_t)n * M, 256), 256, 0, as_stream(stream)>>>(
+        x, ld, M, tidx, n, in, alpha, beta);
+    return check_launch("k_unpack_slices");
+}
+
+}  // extern "C"

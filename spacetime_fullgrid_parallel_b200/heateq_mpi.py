@@ -1,0 +1,211 @@
+"""Operator graph and driver of the parallel-in-time heat-equation solve.
+
+Drop-in for /root/reference/heateq_mpi.py: `HeatEquationMPI` keeps its
+constructor arguments and attributes (`W, WT, S, P, WT_S_W, rhs, Kinv_x, C_j,
+CAC_j, A_MKM, ...`, heateq_mpi.py:126-194), the driver keeps its flags, its
+printed report and the final `data:` blob (:205-312).
+
+What differs is where things live.  The reference assembles with NGSolve on
+the node leader and publishes through MPI shared memory; here the host
+assembler of `assembly.py` stands in for NGSolve (absent from this image; any
+object with the same matrix attributes can be passed as `problem`), and every
+matrix becomes device resident once.  K_x = MG(A_x) and all C_j =
+MG(2^j M_x + alpha A_x) share one `MultiGridFamily`, so P applies all time
+slices in one batched V-cycle.
+
+Run:  python -m spacetime_fullgrid_parallel_b200.heateq_mpi --J_time 3 --J_space 6
+      torchrun --nproc-per-node 2 -m spacetime_fullgrid_parallel_b200.heateq_mpi ...
+"""
+import argparse
+import base64
+import os
+import pickle
+import sys
+import zlib
+
+import numpy as np
+import psutil
+
+from .comm import Wtime, init_from_env, world
+from .linalg import PCG
+from .linop import CompositeLinOp
+from .mpi_kron import (BlockDiagMPI, CompositeMPI, MatKronIdentityMPI, SumMPI,
+                       TridiagKronMatMPI)
+from .mpi_shared_mem import shared_sparse_matrix
+from .mpi_vector import DofDistributionMPI, KronVectorMPI
+from .multigrid import MultiGrid, MultiGridFamily
+from .wavelets import (TransposedWaveletTransformKronIdentityMPI,
+                       WaveletTransformKronIdentityMPI, WaveletTransformOp)
+
+
+def mem():
+    return psutil.Process(os.getpid()).memory_info().rss / 1048576
+
+
+class HeatEquationMPI:
+    def __init__(self, J_space=2, J_time=None, problem='square',
+                 wavelettransform='composite', precond='multigrid',
+                 smoothsteps=3, alpha=0.3, vcycles=2, comm=None, order='class'):
+        comm = world() if comm is None else comm
+        self.shared_comm = comm.Split_type(None)
+        start_time = Wtime()
+        if J_time is None:
+            J_time = J_space
+        self.J_time, self.J_space, self.alpha = J_time, J_space, alpha
+
+        # ---- host assembly (the NGSolve block, heateq_mpi.py:63-104) ----
+        if isinstance(problem, str):
+            if problem != 'square':
+                raise NotImplementedError(
+                    "problem %r: only 'square' has a host assembler here; "
+                    'pass an assembled problem object instead' % problem)
+            from .assembly import SquareProblem
+            problem = SquareProblem(J_space, J_time, alpha=alpha, order=order)
+        prob = self.problem = problem
+        self.N, self.M = prob.N, prob.M
+        self.mem_after_ngsolve = mem()
+        self.dofs_distr = DofDistributionMPI(comm, self.N, self.M)
+
+        # ---- device-resident matrices (heateq_mpi.py:111-123) ----
+        self.A_t, self.L_t, self.M_t, self.G_t = (prob.A_t, prob.L_t, prob.M_t,
+                                                  prob.G_t)
+        self.M_x = shared_sparse_matrix(prob.M_x)
+        self.A_x = shared_sparse_matrix(prob.A_x)
+        self.u0_t, self.u0_x = prob.u0_t, prob.u0_x
+        self.mem_after_shared_matrices = mem()
+
+        # ---- wavelet transform (heateq_mpi.py:127-139) ----
+        if wavelettransform == 'composite':
+            self.W = WaveletTransformKronIdentityMPI(self.dofs_distr, J_time)
+            self.WT = TransposedWaveletTransformKronIdentityMPI(
+                self.dofs_distr, J_time)
+        else:
+            assert wavelettransform in ('original', 'interleaved')
+            self.W_t = WaveletTransformOp(
+                J_time, interleaved=(wavelettransform == 'interleaved'))
+            self.W = MatKronIdentityMPI(self.dofs_distr, self.W_t)
+            self.WT = MatKronIdentityMPI(self.dofs_distr, self.W_t.T)
+
+        # ---- preconditioners in space (heateq_mpi.py:142-162) ----
+        if precond != 'multigrid':
+            raise NotImplementedError(
+                "precond=%r: the device path implements 'multigrid' only" %
+                precond)
+        hierarchy = prob.hierarchy
+        self.family = MultiGridFamily([prob.M_x, prob.A_x], hierarchy,
+                                      smoothsteps=smoothsteps, vcycles=vcycles)
+        self.Kinv_x = self.family.member((0.0, 1.0))
+        self.C_j = [
+            self.family.member((2.0**j, alpha)) for j in range(J_time + 1)
+        ]
+        self.CAC_j = [
+            CompositeLinOp([self.C_j[j], self.A_x, self.C_j[j]])
+            for j in range(J_time + 1)
+        ]
+        self.mem_after_precond = mem()
+
+        # ---- space-time operators (heateq_mpi.py:165-185) ----
+        d = self.dofs_distr
+        K, Mx, Ax = self.Kinv_x, self.M_x, self.A_x
+        self.A_MKM = TridiagKronMatMPI(d, self.A_t, CompositeLinOp([Mx, K, Mx]))
+        self.L_MKA = TridiagKronMatMPI(d, self.L_t, CompositeLinOp([Mx, K, Ax]))
+        self.LT_AKM = TridiagKronMatMPI(d, self.L_t.T.tocsr(),
+                                        CompositeLinOp([Ax, K, Mx]))
+        self.M_AKA = TridiagKronMatMPI(d, self.M_t, CompositeLinOp([Ax, K, Ax]))
+        self.G_M = TridiagKronMatMPI(d, self.G_t, Mx)
+        self.S = SumMPI(
+            d, [self.A_MKM, self.L_MKA, self.LT_AKM, self.M_AKA, self.G_M])
+        self.P = BlockDiagMPI(d, [self.CAC_j[j] for j in self.W.levels])
+        self.WT_S_W = CompositeMPI(d, [self.WT, self.S, self.W])
+
+        # ---- right-hand side (heateq_mpi.py:188-191) ----
+        self.rhs = KronVectorMPI(d)
+        self.rhs.X_loc[:] = np.kron(self.u0_t[self.rhs.t_begin:self.rhs.t_end],
+                                    self.u0_x).reshape(-1, self.M)
+        self.setup_time = Wtime() - start_time
+        self.mem_after_mpi = mem()
+
+    def print_time_per_apply(self):
+        for name in ('W', 'S', 'WT', 'P'):
+            print('{}:{}{:.5f}\t{:.5f}'.format(
+                name, ' ' * (3 - len(name)),
+                *getattr(self, name).time_per_apply()))
+        print('')
+
+
+def main(argv=None):
+    parser = argparse.ArgumentParser(
+        description='Solve heatequation on B200s, parallel in time.')
+    parser.add_argument('--problem', default='square')
+    parser.add_argument('--J_time', type=int, default=7)
+    parser.add_argument('--J_space', type=int, default=7)
+    parser.add_argument('--smoothsteps', type=int, default=3)
+    parser.add_argument('--vcycles', type=int, default=2)
+    parser.add_argument('--wavelettransform', default='composite')
+    parser.add_argument('--alpha', type=float, default=0.3)
+    args = parser.parse_args(argv)
+
+    import torch
+    comm = init_from_env()
+    rank, size = comm.Get_rank(), comm.Get_size()
+    data = {'rank': rank, 'size': size}
+    if size > 2**args.J_time + 1:
+        print('Too many MPI processors!')
+        sys.exit('1')
+    if rank == 0:
+        print('\n\nCreating mesh with {} time refines and {} space refines.'.
+              format(args.J_time, args.J_space))
+        print('MPI tasks: {} '.format(size))
+        print('Arguments: {}'.format(args))
+
+    heq = HeatEquationMPI(J_space=args.J_space, J_time=args.J_time,
+                          problem=args.problem, smoothsteps=args.smoothsteps,
+                          vcycles=args.vcycles, alpha=args.alpha,
+                          wavelettransform=args.wavelettransform, comm=comm)
+    if rank == 0:
+        data['args'] = vars(args)
+        data['N'], data['M'] = heq.N, heq.M
+        print('N = {}. M = {}.'.format(heq.N, heq.M))
+        print('Constructed bilinear forms in {} s.'.format(heq.setup_time))
+        print('Memory after ngsolve: {}mb.'.format(heq.mem_after_ngsolve))
+        print('Memory after shared mat: {}mb.'.format(
+            heq.mem_after_shared_matrices))
+        print('Memory after precond: {}mb.'.format(heq.mem_after_precond))
+        print('Memory after construction: {}mb.'.format(mem()))
+    data['mem_after_construction'] = mem()
+
+    def cb(w, residual, k):
+        if rank == 0:
+            print('.', end='', flush=True)
+
+    torch.cuda.synchronize()
+    comm.Barrier()
+    solve_time = Wtime()
+    u, iters = PCG(heq.WT_S_W, heq.P, heq.rhs, callback=cb)
+    torch.cuda.synchronize()
+    comm.Barrier()
+    data['solve_time'] = Wtime() - solve_time
+    data['mem_after_solve'] = mem()
+    data['iters'] = iters
+    for name in ('W', 'S', 'WT', 'P', 'WT_S_W'):
+        op = getattr(heq, name)
+        data[name] = {
+            'time_applies': op.time_applies,
+            'time_communication': op.time_communication,
+            'num_applies': op.num_applies
+        }
+    if rank == 0:
+        print('')
+        print('Completed in {} PCG steps.'.format(iters))
+        print('Total solve time: {}s.'.format(data['solve_time']))
+        heq.print_time_per_apply()
+        print('Memory after solve: {}mb.'.format(mem()))
+    data = comm.gather(data, root=0)
+    if rank == 0:
+        print('\ndata: {}'.format(
+            str(base64.b64encode(zlib.compress(pickle.dumps(data))), 'ascii')))
+    return u, iters
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,146 @@
+"""Space operators on device blocks.
+
+Mirrors the serial operator layer of /root/reference/source/linop.py that the
+MPI operators consume: `CompositeLinOp` (:68-79, the M.K.A chains of
+heateq_mpi.py:166-178) and the plain CSR matrices passed as `mat_space`.
+Everything acts on (M, ld) device blocks -- all local time slices at once --
+through libstk; there is no host path.
+
+Protocol of a space operator:
+    op.shape                          (M, M)
+    op.apply_block(x, out, ctx=None)  out <- op x   (x, out: (M, ld) device
+                                      tensors, out is not x)
+`ctx` carries per-slice coefficients for operator families (multigrid.py);
+plain operators ignore it.
+"""
+import numpy as np
+import scipy.sparse as sp
+import torch
+
+from ._lib import check, lib, ptr, stream
+
+
+class DeviceCSR:
+    """A CSR matrix resident in HBM (fp64 values, int32 indices, as
+    mpi_shared_mem.py:46-48 stores them)."""
+    def __init__(self, mat, device=None):
+        mat = sp.csr_matrix(mat, dtype=np.float64)
+        mat.sort_indices()
+        if device is None:
+            from .mpi_vector import _device
+            device = _device()
+        self.shape = mat.shape
+        self.nnz = mat.nnz
+        self.host = mat
+        self.indptr = torch.from_numpy(mat.indptr.astype(np.int32)).to(device)
+        self.indices = torch.from_numpy(mat.indices.astype(np.int32)).to(device)
+        self.data = torch.from_numpy(mat.data.astype(np.float64)).to(device)
+        self.num_applies = 0
+
+    def spmm(self, x, out, alpha=1.0, beta=0.0, z=None):
+        """out = alpha * A x + beta * z  on blocks; z may be out."""
+        ld = x.shape[1]
+        check(lib().stk_space_spmm(self.shape[0], ptr(self.indptr),
+                                   ptr(self.indices), 1, ptr(self.data), None,
+                                   None, None, ptr(x), float(alpha),
+                                   float(beta), ptr(z), ptr(out), ld,
+                                   stream()))
+        self.num_applies += 1
+
+    def apply_block(self, x, out, ctx=None):
+        self.spmm(x, out)
+
+    def toarray(self):
+        return self.host.toarray()
+
+    def tocsr(self):
+        return self.host
+
+    def __matmul__(self, B):
+        """Host arrays (M,) / (M, k), computed on the device."""
+        return host_apply(self, B)
+
+
+_csr_cache = {}
+
+
+def as_space_op(op):
+    """Device form of whatever the reference accepts as `mat_space`: a scipy
+    sparse matrix (uploaded once, cached), or an object that already follows
+    the protocol (DeviceCSR, MultiGrid, CompositeLinOp)."""
+    if hasattr(op, 'apply_block'):
+        return op
+    if sp.issparse(op) or isinstance(op, np.ndarray):
+        key = id(op)
+        if key not in _csr_cache:
+            _csr_cache[key] = (op, DeviceCSR(op))
+        return _csr_cache[key][1]
+    raise TypeError(
+        'space operator %r has no device form: pass a scipy sparse matrix, '
+        'shared_sparse_matrix(...), MultiGrid or CompositeLinOp (the B200 path '
+        'has no CPU fallback for generic LinearOperators)' % type(op))
+
+
+class CompositeLinOp:
+    """x -> linops[0] (linops[1] (... linops[-1] x)) (linop.py:68-79)."""
+    def __init__(self, linops):
+        self.linops = [as_space_op(l) for l in linops]
+        for a, b in zip(self.linops[:-1], self.linops[1:]):
+            assert a.shape[1] == b.shape[0]
+        self.shape = (self.linops[0].shape[0], self.linops[-1].shape[1])
+
+    def apply_block(self, x, out, ctx=None):
+        ops = self.linops[::-1]
+        cur = x
+        for k, op in enumerate(ops):
+            last = k == len(ops) - 1
+            if last:
+                dst = out
+            else:
+                rows = op.shape[0]
+                dst = torch.empty((rows, x.shape[1]), dtype=x.dtype,
+                                  device=x.device)
+            op.apply_block(cur, dst)
+            cur = dst
+
+    # scipy-style host interface (tests): (M,) or (M, k) arrays
+    def __matmul__(self, B):
+        return host_apply(self, B)
+
+
+class KronLinOp:
+    """Serial (mat_time (x) mat_space) x on a host vector of N*M entries
+    (linop.py:6-15), computed on the device."""
+    def __init__(self, mat_time, mat_space):
+        self.mat_time = sp.csr_matrix(mat_time)
+        self.mat_space = as_space_op(mat_space)
+        self.N, self.M = self.mat_time.shape[0], self.mat_space.shape[0]
+        self.shape = (self.N * self.M, self.N * self.M)
+
+    def __matmul__(self, x):
+        from .comm import SerialComm
+        from .mpi_kron import TridiagKronMatMPI
+        from .mpi_vector import DofDistributionMPI, KronVectorMPI
+        d = DofDistributionMPI(SerialComm(), self.N, self.M)
+        op = TridiagKronMatMPI(d, self.mat_time, self.mat_space)
+        v = KronVectorMPI(d, np.asarray(x, dtype=np.float64).reshape(
+            self.N, self.M))
+        return (op @ v).to_host().reshape(-1)
+
+
+def host_apply(op, B):
+    """`op @ B` for host arrays (M,) or (M, k): columns are the batch, which
+    is exactly the time-fastest block layout."""
+    from .mpi_vector import _device, pitch
+    B = np.asarray(B, dtype=np.float64)
+    one = B.ndim == 1
+    B2 = B.reshape(B.shape[0], -1)
+    k = B2.shape[1]
+    ld = pitch(k)
+    dev = _device()
+    x = torch.zeros((B2.shape[0], ld), dtype=torch.float64, device=dev)
+    x[:, :k] = torch.from_numpy(np.ascontiguousarray(B2)).to(dev)
+    out = torch.empty((op.shape[0], ld), dtype=torch.float64, device=dev)
+    op.apply_block(x, out)
+    res = out[:, :k].cpu().numpy()
+    return res[:, 0].copy() if one else res

@@ -1,0 +1,254 @@
+"""Space multigrid V-cycle preconditioner, batched over time slices on the GPU.
+
+Drop-in for `MultiGrid` of /root/reference/source/multigrid.py:130-197:
+same constructor `MultiGrid(mat, hierarchy, smoothsteps=2, vcycles=1)`, same
+Galerkin hierarchy (:140-145), lexicographic Gauss-Seidel pre/post smoothing
+(PETSc MatSOR, :100-127), exact coarsest solve (:161-170), `vcycles` cycles
+from a zero guess (:184-193).  `hierarchy` is duck-typed: `.J`, `.P_mats`,
+`.R_mats` (what MeshHierarchy :14-80 provides).
+
+Difference in kind, not in result: the reference runs one slice at a time
+through Python; here one launch sequence serves every local time slice, and a
+`MultiGridFamily` serves every matrix of the form  sum_k c_k B_k  (K_x = MG(A_x)
+and all C_j = MG(2^j M_x + alpha A_x), heateq_mpi.py:143-153) from ONE
+device-resident hierarchy with per-slice coefficients.
+"""
+import ctypes
+
+import numpy as np
+import scipy.sparse as sp
+import torch
+
+from ._lib import check, lib, ptr, stream
+from .linop import host_apply
+from .mpi_vector import _device
+
+MAX_COARSE = 1024
+
+
+def _project(pattern_keys, mat, ncols):
+    """Values of `mat` laid out on the (sorted) union pattern."""
+    mat = sp.csr_matrix(mat)
+    mat.sort_indices()
+    rows = np.repeat(np.arange(mat.shape[0], dtype=np.int64),
+                     np.diff(mat.indptr))
+    keys = rows * ncols + mat.indices
+    pos = np.searchsorted(pattern_keys, keys)
+    vals = np.zeros(len(pattern_keys))
+    vals[pos] = mat.data
+    return vals
+
+
+def gauss_seidel_schedule(indptr, indices):
+    """Wavefronts of the lexicographic sweep: (rows ordered wavefront by
+    wavefront, phase_ptr).  Host, setup only."""
+    n = len(indptr) - 1
+    indptr = np.ascontiguousarray(indptr, dtype=np.int32)
+    indices = np.ascontiguousarray(indices, dtype=np.int32)
+    wave = np.zeros(max(n, 1), dtype=np.int32)
+    depth = lib().stk_gs_wavefronts(n, indptr.ctypes.data,
+                                    indices.ctypes.data, wave.ctypes.data)
+    wave = wave[:n]
+    order = np.argsort(wave, kind='stable').astype(np.int32)
+    counts = np.bincount(wave, minlength=max(depth, 1))
+    phase_ptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    return order, phase_ptr
+
+
+class MGContext:
+    """Per-slice coefficients of a block with pitch ld (device arrays)."""
+    def __init__(self, family, coefs_per_slice, ld):
+        n = len(coefs_per_slice)
+        assert 1 <= n <= ld
+        dev = family.device
+        K = family.K
+        distinct = []
+        group = np.zeros(ld, dtype=np.int32)
+        table = np.zeros((K, ld))
+        for t in range(ld):
+            c = tuple(float(v) for v in coefs_per_slice[min(t, n - 1)])
+            assert len(c) == K
+            if c not in distinct:
+                distinct.append(c)
+            group[t] = distinct.index(c)
+            table[:, t] = c
+        inv = np.stack([family.coarse_inverse(c) for c in distinct])
+        self.coef = [torch.from_numpy(table[k].copy()).to(dev)
+                     for k in range(K)]
+        self.inv = torch.from_numpy(np.ascontiguousarray(inv)).to(dev)
+        self.group = torch.from_numpy(group).to(dev)
+        self.ld = ld
+
+
+_ws = {}
+
+
+def _workspace(device, doubles):
+    cur = _ws.get(device)
+    if cur is None or cur.numel() < doubles:
+        _ws[device] = None
+        cur = _ws[device] = torch.empty(int(doubles), dtype=torch.float64,
+                                        device=device)
+    return cur
+
+
+class MultiGridFamily:
+    """All V-cycle preconditioners MG(sum_k c_k base_mats[k]) on one mesh
+    hierarchy, K = len(base_mats) in {1, 2}."""
+    def __init__(self, base_mats, hierarchy, smoothsteps=2, vcycles=1,
+                 device=None):
+        self.K = K = len(base_mats)
+        assert K in (1, 2)
+        self.hierarchy = hierarchy
+        self.smoothsteps, self.vcycles = smoothsteps, vcycles
+        self.device = dev = _device() if device is None else device
+        J = hierarchy.J
+        # Galerkin hierarchies, coarse from fine (multigrid.py:140-145)
+        mats = []
+        for B in base_mats:
+            lv = [sp.csr_matrix(B, dtype=np.float64)]
+            for j in reversed(range(J)):
+                lv.insert(0, (hierarchy.R_mats[j] @ lv[0]
+                              @ hierarchy.P_mats[j]).tocsr())
+            mats.append(lv)
+        self.level_mats = mats
+        self.shape = mats[0][-1].shape
+        n0 = mats[0][0].shape[0]
+        if n0 > MAX_COARSE:
+            raise ValueError('coarsest level has %d dofs (> %d): the dense '
+                             'coarse solve needs a coarser mesh' %
+                             (n0, MAX_COARSE))
+        self._inv_cache = {}
+        self._ctx_cache = {}
+        self._keep = []  # device tensors referenced by the C handle
+        self.handle = ctypes.c_void_p(
+            lib().stk_mg_create(J + 1, smoothsteps, vcycles, K))
+        assert self.handle.value, 'stk_mg_create failed'
+        self.num_phases = []
+
+        def up(a, dt):
+            t = torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(dev)
+            self._keep.append(t)
+            return t
+
+        for l in range(J + 1):
+            n = mats[0][l].shape[0]
+            pat = mats[0][l].copy()
+            pat.data = np.ones_like(pat.data)
+            for k in range(1, K):
+                q = mats[k][l].copy()
+                q.data = np.ones_like(q.data)
+                pat = pat + q
+            pat = pat.tocsr()
+            pat.sort_indices()
+            rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(pat.indptr))
+            keys = rows * n + pat.indices
+            vals = [_project(keys, mats[k][l], n) for k in range(K)]
+            diags = [mats[k][l].diagonal() for k in range(K)]
+            order, phase_ptr = gauss_seidel_schedule(pat.indptr, pat.indices)
+            self.num_phases.append(len(phase_ptr) - 1)
+            d_indptr, d_indices = up(pat.indptr, np.int32), up(
+                pat.indices, np.int32)
+            d_vals = [up(v, np.float64) for v in vals]
+            d_diag = [up(d, np.float64) for d in diags]
+            d_order = up(order, np.int32)
+            check(lib().stk_mg_set_level(
+                self.handle, l, n, ptr(d_indptr), ptr(d_indices),
+                ptr(d_vals[0]), ptr(d_vals[1]) if K == 2 else None,
+                ptr(d_diag[0]), ptr(d_diag[1]) if K == 2 else None,
+                ptr(d_order), phase_ptr.ctypes.data, len(phase_ptr) - 1))
+            if l >= 1:
+                P = sp.csr_matrix(hierarchy.P_mats[l - 1], dtype=np.float64)
+                R = sp.csr_matrix(hierarchy.R_mats[l - 1], dtype=np.float64)
+                P.sort_indices()
+                R.sort_indices()
+                tp = [up(P.indptr, np.int32), up(P.indices, np.int32),
+                      up(P.data, np.float64), up(R.indptr, np.int32),
+                      up(R.indices, np.int32), up(R.data, np.float64)]
+                check(lib().stk_mg_set_transfer(self.handle, l,
+                                                *[ptr(t) for t in tp]))
+
+    def __del__(self):
+        try:
+            if self.handle and self.handle.value:
+                lib().stk_mg_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def coarse_inverse(self, coefs):
+        """Dense inverse of the coarsest matrix (the reference factorises it
+        with SuperLU, multigrid.py:161-165; it is 1x1 for `square`)."""
+        coefs = tuple(float(c) for c in coefs)
+        if coefs not in self._inv_cache:
+            A0 = sum(c * self.level_mats[k][0].toarray()
+                     for k, c in enumerate(coefs))
+            self._inv_cache[coefs] = np.linalg.inv(A0)
+        return self._inv_cache[coefs]
+
+    def context(self, coefs_per_slice, ld):
+        key = (tuple(tuple(float(v) for v in c) for c in coefs_per_slice), ld)
+        if key not in self._ctx_cache:
+            self._ctx_cache[key] = MGContext(self, coefs_per_slice, ld)
+        return self._ctx_cache[key]
+
+    def apply_block(self, b, x, ctx):
+        """x <- MG(A(t)) b for every slice t of the block."""
+        ld = b.shape[1]
+        assert ctx.ld == ld and b.shape[0] == self.shape[0]
+        ws = _workspace(b.device, lib().stk_mg_workspace(self.handle, ld))
+        c0 = ptr(ctx.coef[0]) if self.K == 2 else None
+        c1 = ptr(ctx.coef[1]) if self.K == 2 else None
+        check(lib().stk_mg_apply(self.handle, c0, c1, ptr(ctx.inv),
+                                 ptr(ctx.group), ptr(b), ptr(x), ld, ptr(ws),
+                                 stream()))
+
+    def member(self, coefs):
+        """The MultiGrid operator of sum_k coefs[k] * base_mats[k]."""
+        return MultiGrid(None, self.hierarchy, self.smoothsteps, self.vcycles,
+                         _family=self, _coefs=coefs)
+
+
+class MultiGrid:
+    """V-cycle preconditioner for one matrix (multigrid.py:130-197)."""
+    def __init__(self, mat, hierarchy, smoothsteps=2, vcycles=1, _family=None,
+                 _coefs=None):
+        self.num_applies = 0
+        self.time_applies = 0
+        self.hierarchy = hierarchy
+        self.smoothsteps = smoothsteps
+        self.vcycles = vcycles
+        if _family is None:
+            _family = MultiGridFamily([mat], hierarchy, smoothsteps, vcycles)
+            _coefs = (1.0, )
+        self.family = _family
+        self.coefs = tuple(float(c) for c in _coefs)
+        assert len(self.coefs) == _family.K
+        self.shape = _family.shape
+        self.dtype = np.dtype(np.float64)
+
+    @property
+    def mats(self):
+        """Level matrices, coarse to fine (multigrid.py:140-154)."""
+        lm = self.family.level_mats
+        return [
+            sum(c * lm[k][l] for k, c in enumerate(self.coefs))
+            for l in range(len(lm[0]))
+        ]
+
+    def apply_block(self, x, out, ctx=None):
+        if ctx is None:
+            ld = x.shape[1]
+            ctx = self.family.context([self.coefs], ld)
+        self.family.apply_block(x, out, ctx)
+        self.num_applies += 1
+
+    # SciPy LinearOperator-style host interface (M,) / (M, k)
+    def __matmul__(self, B):
+        return host_apply(self, B)
+
+    matvec = matmat = dot = _matvec = __matmul__
+
+    def time_per_apply(self):
+        assert self.time_applies
+        return self.time_applies / self.num_applies

@@ -1,0 +1,198 @@
+"""Sparse operators along the (sharded) time axis: (T (x) I) x and (T^T (x) I) x.
+
+One mechanism serves the reference's three flavours of time coupling
+(SURVEY.md 2b): the +-1-slice halo of `TridiagKronIdentityMPI`
+(mpi_kron.py:153-201, mpi_vector.py:140-187), the per-level sparse row
+exchange of `SparseKronIdentityMPI` (mpi_kron.py:259-317,
+mpi_vector.py:189-203) and, with all wavelet levels multiplied together, the
+whole wavelet transform in ONE exchange of <= 2J-1 boundary slices.
+
+`TimeOpPlan` is host logic (numpy only, testable under gloo on CPU): which
+global time slices this rank needs from / owes to which peer, and the local
+CSR with its columns renumbered [local | halo].  `fetch`, `apply` and
+`apply_adjoint` run it on the device through libstk.
+"""
+import numpy as np
+import scipy.sparse as sp
+
+
+class TimeOpPlan:
+    def __init__(self, dofs_distr, T):
+        T = sp.csr_matrix(T, dtype=np.float64)
+        d = self.dofs_distr = dofs_distr
+        N = d.N
+        assert T.shape == (N, N)
+        a, b = d.t_begin, d.t_end
+        self.n_loc = n = b - a
+        bounds = d.dof_distribution
+        loc = T[a:b].tocsr()
+        loc.sort_indices()
+        cols = np.unique(loc.indices)
+        remote = cols[(cols < a) | (cols >= b)]
+        self.halo_cols = remote  # sorted, hence grouped by owner rank
+        self.n_halo = len(remote)
+        # recv_from[p] = (offset, count) into the halo list
+        self.recv_from = {}
+        for p, (pa, pb) in enumerate(bounds):
+            if p == d.rank:
+                continue
+            sel = np.nonzero((remote >= pa) & (remote < pb))[0]
+            if len(sel):
+                self.recv_from[p] = (int(sel[0]), len(sel))
+        # send_to[p] = local indices of my slices that rank p's rows touch
+        self.send_to = {}
+        for p, (pa, pb) in enumerate(bounds):
+            if p == d.rank:
+                continue
+            theirs = np.unique(T[pa:pb].indices)
+            mine = theirs[(theirs >= a) & (theirs < b)]
+            if len(mine):
+                self.send_to[p] = (mine - a).astype(np.int32)
+        # local CSR, columns renumbered: local t -> t-a, halo k -> n + k
+        remap = np.full(N, -1, dtype=np.int64)
+        remap[a:b] = np.arange(n)
+        remap[remote] = n + np.arange(len(remote))
+        self.local = sp.csr_matrix(
+            (loc.data, remap[loc.indices].astype(np.int32), loc.indptr),
+            shape=(n, n + len(remote)))
+        # adjoint: (T_loc)^T split into the rows that stay here and the rows
+        # that belong to the halo owners
+        lt = self.local.T.tocsr()
+        lt.sort_indices()
+        self.adj_local = lt[:n].tocsr()
+        self.adj_halo = lt[n:].tocsr()
+        self._dev = None
+
+    # -- device execution --------------------------------------------------
+    def _device_arrays(self, device):
+        import torch
+        if self._dev is None or self._dev['device'] != device:
+
+            def csr(m):
+                return (torch.from_numpy(m.indptr.astype(np.int32)).to(device),
+                        torch.from_numpy(m.indices.astype(np.int32)).to(device),
+                        torch.from_numpy(m.data.astype(np.float64)).to(device))
+
+            self._dev = {
+                'device': device,
+                'local': csr(self.local),
+                'adj_local': csr(self.adj_local),
+                'adj_halo': csr(self.adj_halo),
+                'send_idx': {
+                    p: torch.from_numpy(idx).to(device)
+                    for p, idx in self.send_to.items()
+                },
+                'halo_iota': torch.arange(self.n_halo, dtype=torch.int32,
+                                          device=device),
+            }
+        return self._dev
+
+    def fetch(self, vec, callback=None):
+        """Halo slices of `vec` as an (n_halo, M) slice-major device buffer;
+        cached on the vector until it is written (mpi_vector.py:143-145)."""
+        import torch
+        from ._lib import check, lib, ptr, stream
+        key = ('halo', self.halo_cols.tobytes(),
+               tuple(sorted((p, v.tobytes()) for p, v in self.send_to.items())))
+        if key in vec._halo:
+            if callback is not None:
+                callback()
+            return vec._halo[key]
+        dev = self._device_arrays(vec.data.device)
+        M = vec.M
+        halo = torch.empty((self.n_halo, M), dtype=torch.float64,
+                           device=vec.data.device)
+        sends, recvs = {}, {}
+        for p, idx in dev['send_idx'].items():
+            buf = torch.empty((len(idx), M), dtype=torch.float64,
+                              device=vec.data.device)
+            check(lib().stk_pack_slices(ptr(vec.data), vec.ld, M, ptr(idx),
+                                        len(idx), ptr(buf), stream()))
+            sends[p] = buf
+        for p, (off, cnt) in self.recv_from.items():
+            recvs[p] = halo[off:off + cnt]
+        if callback is not None:
+            callback()
+        t0 = _now()
+        vec.dofs_distr.comm.exchange(sends, recvs)
+        self.time_communication = getattr(self, 'time_communication',
+                                          0.0) + _now() - t0
+        vec._halo[key] = halo
+        return halo
+
+    def apply(self, vec_in, out_block, alpha=1.0, beta=0.0):
+        """out_block = alpha * (T (x) I) vec_in + beta * out_block."""
+        from ._lib import check, lib, ptr, stream
+        dev = self._device_arrays(vec_in.data.device)
+        halo = self.fetch(vec_in) if self.n_halo else None
+        indptr, indices, vals = dev['local']
+        check(lib().stk_time_apply(vec_in.M, self.n_loc, ptr(indptr),
+                                   ptr(indices), ptr(vals), ptr(vec_in.data),
+                                   vec_in.ld, self.n_loc, ptr(halo),
+                                   float(alpha), float(beta), ptr(out_block),
+                                   vec_in.ld, stream()))
+
+    def apply_adjoint(self, vec_in, vec_out):
+        """vec_out = (T^T (x) I) vec_in: local partial sums, then the partial
+        sums that belong to other ranks' slices are sent there and added (the
+        adjoint of `fetch`)."""
+        import torch
+        from ._lib import check, lib, ptr, stream
+        from .mpi_vector import pitch
+        dev = self._device_arrays(vec_in.data.device)
+        M, n = vec_in.M, self.n_loc
+        vec_out._invalidate()
+        indptr, indices, vals = dev['adj_local']
+        check(lib().stk_time_apply(M, n, ptr(indptr), ptr(indices), ptr(vals),
+                                   ptr(vec_in.data), vec_in.ld, n, None, 1.0,
+                                   0.0, ptr(vec_out.data), vec_out.ld,
+                                   stream()))
+        if not self.n_halo and not self.send_to:
+            return
+        sends, recvs = {}, {}
+        if self.n_halo:
+            ldh = pitch(self.n_halo)
+            part = torch.empty((M, ldh), dtype=torch.float64,
+                               device=vec_in.data.device)
+            indptr, indices, vals = dev['adj_halo']
+            check(lib().stk_time_apply(M, self.n_halo, ptr(indptr),
+                                       ptr(indices), ptr(vals),
+                                       ptr(vec_in.data), vec_in.ld, n, None,
+                                       1.0, 0.0, ptr(part), ldh, stream()))
+            packed = torch.empty((self.n_halo, M), dtype=torch.float64,
+                                 device=vec_in.data.device)
+            check(lib().stk_pack_slices(ptr(part), ldh, M,
+                                        ptr(dev['halo_iota']), self.n_halo,
+                                        ptr(packed), stream()))
+            for p, (off, cnt) in self.recv_from.items():
+                sends[p] = packed[off:off + cnt]
+        for p, idx in dev['send_idx'].items():
+            recvs[p] = torch.empty((len(idx), M), dtype=torch.float64,
+                                   device=vec_in.data.device)
+        t0 = _now()
+        vec_in.dofs_distr.comm.exchange(sends, recvs)
+        self.time_communication = getattr(self, 'time_communication',
+                                          0.0) + _now() - t0
+        for p, idx in dev['send_idx'].items():
+            check(lib().stk_unpack_slices(ptr(vec_out.data), vec_out.ld, M,
+                                          ptr(idx), len(idx), ptr(recvs[p]),
+                                          1.0, 1.0, stream()))
+
+
+def _now():
+    import time
+    return time.perf_counter()
+
+
+_neighbour_plans = {}
+
+
+def neighbour_plan(dofs_distr):
+    """The +-1 halo of every tridiagonal time matrix (mpi_vector.py:140-187)."""
+    key = id(dofs_distr)
+    if key not in _neighbour_plans:
+        N = dofs_distr.N
+        T = sp.diags([np.ones(N - 1), np.ones(N), np.ones(N - 1)], [-1, 0, 1],
+                     format='csr') if N > 1 else sp.identity(1, format='csr')
+        _neighbour_plans[key] = (dofs_distr, TimeOpPlan(dofs_distr, T))
+    return _neighbour_plans[key][1]

@@ -177,8 +177,9 @@ def wavelet_split(J, j):
 # ---------------------------------------------------------------------------
 class MultiGridOracle:
     """V-cycle preconditioner on slice blocks X of shape (k, M)."""
-    def __init__(self, mat, P_mats, smoothsteps=2, vcycles=1):
+    def __init__(self, mat, P_mats, smoothsteps=2, vcycles=1, threads=1):
         self.nu, self.vcycles = smoothsteps, vcycles
+        self.threads = threads
         self.P = [sp.csr_matrix(P) for P in P_mats]
         self.R = [P.T.tocsr() for P in self.P]  # multigrid.py:60
         self.mats = [sp.csr_matrix(mat)]
@@ -213,6 +214,19 @@ class MultiGridOracle:
         """(k, M) -> (k, M): `vcycles` V-cycles from a zero initial guess
         (multigrid.py:184-193)."""
         F = np.ascontiguousarray(X, dtype=np.float64)
+        if self.threads > 1 and F.shape[0] > 1:
+            # the slices are independent (the reference's ranks each own a
+            # slab of them): one chunk of slices per host thread
+            from concurrent.futures import ThreadPoolExecutor
+            chunks = np.array_split(np.arange(F.shape[0]),
+                                    min(self.threads, F.shape[0]))
+            with ThreadPoolExecutor(len(chunks)) as pool:
+                parts = list(pool.map(lambda c: self._solve(F[c]), chunks))
+            return np.concatenate(parts, axis=0)
+        return self._solve(F)
+
+    def _solve(self, F):
+        F = np.ascontiguousarray(F)
         U = np.zeros_like(F)
         for _ in range(self.vcycles):
             self._cycle(len(self.mats) - 1, U, F)
@@ -230,13 +244,14 @@ class MultiGridOracle:
 # the operator graph of heateq_mpi.py:126-191
 # ---------------------------------------------------------------------------
 class HeatEqOracle:
-    def __init__(self, prob, smoothsteps=3, vcycles=2, interleaved=True):
+    def __init__(self, prob, smoothsteps=3, vcycles=2, interleaved=True,
+                 threads=1):
         p = self.prob = prob
         P_mats = p.hierarchy.P_mats
         self.J = p.J_time
         self.interleaved = interleaved
-        self.K = MultiGridOracle(p.A_x, P_mats, smoothsteps, vcycles)
-        self.C = [MultiGridOracle(m, P_mats, smoothsteps, vcycles)
+        self.K = MultiGridOracle(p.A_x, P_mats, smoothsteps, vcycles, threads)
+        self.C = [MultiGridOracle(m, P_mats, smoothsteps, vcycles, threads)
                   for m in p.Cinv_j]
         self.levels = wavelet_levels(self.J, interleaved)
         K, Mx, Ax = self.K, p.M_x, p.A_x

@@ -1,0 +1,180 @@
+"""CPU: host-side logic of the product (partition, exchange plans, wavelet
+matrices, Gauss-Seidel schedule, host assembler) and the C ABI surface.
+No kernel is launched here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import scipy.sparse as sp
+
+from conftest import ROOT, rand, rel
+from oracle import restate as orc
+from spacetime_fullgrid_parallel_b200 import _lib
+from spacetime_fullgrid_parallel_b200.assembly import SquareProblem
+from spacetime_fullgrid_parallel_b200.comm import SerialComm
+from spacetime_fullgrid_parallel_b200.mpi_vector import (DofDistributionMPI,
+                                                         pitch)
+from spacetime_fullgrid_parallel_b200.timeop import TimeOpPlan
+from spacetime_fullgrid_parallel_b200.wavelets import (WaveletTransformOp,
+                                                       levelwise_positions,
+                                                       wavelet_levels)
+
+
+class FakeComm(SerialComm):
+    def __init__(self, rank, size):
+        self.rank, self.size = rank, size
+
+    def Get_rank(self):
+        return self.rank
+
+    def Get_size(self):
+        return self.size
+
+
+def test_abi_exports_every_declared_symbol():
+    """libstk.so loads and exports exactly what include/stk.h declares."""
+    hdr = open(os.path.join(ROOT, 'include', 'stk.h')).read()
+    hdr = re.sub(r'/\*.*?\*/', '', hdr, flags=re.S)
+    declared = set(re.findall(r'\b(stk_[a-z0-9_]+)\s*\(', hdr))
+    assert len(declared) >= 25
+    lib = _lib.lib()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert lib.stk_version() == 100
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    monkeypatch.setattr(_lib, '_lib', None)
+    monkeypatch.setattr(_lib, 'LIB', '/nonexistent/libstk.so')
+    try:
+        _lib.lib()
+    except _lib.StkError as e:
+        assert 'no CPU fallback' in str(e)
+    else:
+        raise AssertionError('expected StkError')
+
+
+def test_dof_distribution():
+    """mpi_vector.py:18-38."""
+    for N, P in ((9, 2), (257, 8), (1025, 8), (5, 5), (13, 3)):
+        bounds = orc.slab_bounds(N, P)
+        for r in range(P):
+            d = DofDistributionMPI(FakeComm(r, P), N, 7)
+            assert (d.t_begin, d.t_end) == bounds[r]
+            assert [tuple(b) for b in d.dof_distribution] == bounds
+            assert d.counts.sum() == N * 7 and d.displs[r] == bounds[r][0] * 7
+            assert all(d.dof2proc[a:b].tolist() == [p] * (b - a)
+                       for p, (a, b) in enumerate(bounds))
+    assert pitch(1) == 4 and pitch(4) == 4 and pitch(33) == 36 and pitch(257) == 260
+
+
+def _emulate(T, P, M=3, adjoint=False):
+    """Run the plans of all P ranks with numpy standing in for the device."""
+    N = T.shape[0]
+    X = rand((N, M), seed=N + P)
+    plans = [TimeOpPlan(DofDistributionMPI(FakeComm(r, P), N, M), T)
+             for r in range(P)]
+    bounds = plans[0].dofs_distr.dof_distribution
+    out = np.zeros((N, M))
+    if not adjoint:
+        for r, pl in enumerate(plans):
+            a, b = bounds[r]
+            halo = np.zeros((pl.n_halo, M))
+            for p, (off, cnt) in pl.recv_from.items():
+                # what rank p packs for r must be what r expects, in order
+                sent = X[bounds[p][0] + plans[p].send_to[r]]
+                assert np.array_equal(bounds[p][0] + plans[p].send_to[r],
+                                      pl.halo_cols[off:off + cnt])
+                halo[off:off + cnt] = sent
+            assert set(pl.recv_from) == {p for p in range(P)
+                                         if r in plans[p].send_to}
+            out[a:b] = pl.local @ np.concatenate([X[a:b], halo])
+        return out, T @ X
+    for r, pl in enumerate(plans):
+        a, b = bounds[r]
+        out[a:b] += pl.adj_local @ X[a:b]
+        part = pl.adj_halo @ X[a:b]
+        for p, (off, cnt) in pl.recv_from.items():
+            out[bounds[p][0] + plans[p].send_to[r]] += part[off:off + cnt]
+    return out, T.T @ X
+
+
+def test_timeop_plans():
+    N = 17
+    tri = sp.diags([rand((N - 1, 1), 1)[:, 0], rand((N, 1), 2)[:, 0],
+                    rand((N - 1, 1), 3)[:, 0]], [-1, 0, 1], format='csr')
+    W = WaveletTransformOp(4, interleaved=True).as_matrix()
+    G = sp.csr_matrix(([1.0], ([0], [0])), shape=(N, N))
+    for T in (tri, W, G, sp.identity(N, format='csr')):
+        for P in (1, 2, 3, 4, 8, 17):
+            got, ref = _emulate(T, P)
+            assert rel(got, ref) < 1e-14
+            got, ref = _emulate(T, P, adjoint=True)
+            assert rel(got, ref) < 1e-14
+
+
+def test_wavelet_halo_is_small():
+    """W needs at most 2J-1 remote slices per rank."""
+    for J, P in ((8, 8), (10, 8), (6, 4)):
+        W = WaveletTransformOp(J, interleaved=True).as_matrix()
+        for r in range(P):
+            pl = TimeOpPlan(DofDistributionMPI(FakeComm(r, P), 2**J + 1, 1), W)
+            assert pl.n_halo <= 2 * J - 1
+
+
+def test_wavelet_matrices(golden):
+    g = golden['wavelets']
+    for J in range(1, 7):
+        X = rand((2**J + 1, 3), seed=J)
+        for inter, tag in ((True, 'int'), (False, 'lvl')):
+            op = WaveletTransformOp(J, interleaved=inter)
+            assert np.array_equal(op.levels, g['levels_J%d_%s' % (J, tag)])
+            assert np.array_equal(op.levels, orc.wavelet_levels(J, inter))
+            assert rel(op.as_matrix() @ X, g['W_J%d_%s' % (J, tag)]) < 1e-14
+            assert rel(op.T.as_matrix() @ X, g['WT_J%d_%s' % (J, tag)]) < 1e-14
+    op = WaveletTransformOp(4, interleaved=True)
+    for j in range(1, 5):
+        assert rel(op.split(j).toarray(), g['split_J4_j%d' % j]) < 1e-15
+    assert sorted(levelwise_positions(5)) == list(range(33))
+    assert np.array_equal(wavelet_levels(3, True)[levelwise_positions(3)],
+                          wavelet_levels(3, False))
+
+
+def test_gauss_seidel_schedule():
+    """Wavefronts respect the lexicographic dependencies; the class ordering
+    gives <= 4 wavefronts on every level (assembly.py)."""
+    from spacetime_fullgrid_parallel_b200.multigrid import gauss_seidel_schedule
+    for order, max_depth in (('class', 4), ('lex', None), ('random', None)):
+        prob = SquareProblem(4, 1, order=order, seed=3)
+        A = prob.M_x
+        rows, phase_ptr = gauss_seidel_schedule(A.indptr, A.indices)
+        assert sorted(rows.tolist()) == list(range(A.shape[0]))
+        wave = np.empty(A.shape[0], dtype=int)
+        for ph in range(len(phase_ptr) - 1):
+            wave[rows[phase_ptr[ph]:phase_ptr[ph + 1]]] = ph
+        coo = A.tocoo()
+        off = coo.row != coo.col
+        lo, hi = np.minimum(coo.row, coo.col)[off], np.maximum(coo.row,
+                                                               coo.col)[off]
+        assert np.all(wave[lo] < wave[hi])
+        if max_depth:
+            assert len(phase_ptr) - 1 <= max_depth
+
+
+def test_assembler():
+    """Row sums / symmetry / sizes of the host assembler (stands in for
+    NGSolve, heateq_mpi.py:63-104)."""
+    prob = SquareProblem(3, 2)
+    assert prob.M == (2**4 - 1)**2 and prob.N == 5
+    for A in (prob.M_x, prob.A_x, prob.A_t, prob.M_t):
+        assert abs(A - A.T).max() < 1e-14
+    assert abs(prob.M_t.sum() - 1.0) < 1e-14  # int_0^1 1 dt
+    assert abs(prob.A_t.sum()) < 1e-12
+    assert abs((prob.L_t + prob.L_t.T).toarray() - np.diag(
+        [-1] + [0] * (prob.N - 2) + [1])).max() < 1e-14
+    ones = np.ones(prob.N)
+    assert abs(ones @ (prob.L_t @ ones)) < 1e-14
+    assert prob.A_x.getnnz(axis=1).max() == 5  # zeros eliminated
+    assert prob.M_x.getnnz(axis=1).max() == 7

@@ -14,6 +14,7 @@
 namespace stk {
 
 // y[i,t] = alpha * (A x)[i,t] + beta * z[i,t]; K=2: A(t) = c0[t] A0 + c1[t] A1.
+// Grid-stride over (row, double2 column) items with a resident grid.
 template <int K, bool HAS_Z>
 __global__ void __launch_bounds__(256)
     k_space_spmm(int nrows, const int *__restrict__ indptr, const int *__restrict__ indices,
@@ -21,62 +22,39 @@ __global__ void __launch_bounds__(256)
                  const double *__restrict__ coef0, const double *__restrict__ coef1,
                  const double *__restrict__ x, double alpha, double beta, const double *z,
                  double *y, int ld, unsigned ld2) {
-    unsigned k = blockIdx.x * 256u + threadIdx.x;
-    unsigned i = k / ld2;
-    if (i >= (unsigned)nrows) return;
-    unsigned c = (k - i * ld2) * 2u;
-    int p0 = __ldg(indptr + i), p1 = __ldg(indptr + i + 1);
-    double2 s0 = make_double2(0.0, 0.0), s1 = make_double2(0.0, 0.0);
-    for (int p = p0; p < p1; ++p) {
-        int j = __ldg(indices + p);
-        double2 xv = ldv2(x + (size_t)j * ld + c);
-        double a0 = __ldg(vals0 + p);
-        s0.x = fma(a0, xv.x, s0.x);
-        s0.y = fma(a0, xv.y, s0.y);
+    const unsigned total = (unsigned)nrows * ld2;
+    const unsigned stride = gridDim.x * 256u;
+    for (unsigned k = blockIdx.x * 256u + threadIdx.x; k < total; k += stride) {
+        unsigned i = k / ld2;
+        unsigned c = (k - i * ld2) * 2u;
+        int p0 = __ldg(indptr + i), p1 = __ldg(indptr + i + 1);
+        double2 s0 = make_double2(0.0, 0.0), s1 = make_double2(0.0, 0.0);
+        row_product<K, 0>(p0, p1, indices, vals0, vals1, x, ld, c, s0, s1);
         if (K == 2) {
-            double a1 = __ldg(vals1 + p);
-            s1.x = fma(a1, xv.x, s1.x);
-            s1.y = fma(a1, xv.y, s1.y);
+            double2 c0 = ldg2(coef0 + c), c1 = ldg2(coef1 + c);
+            s0.x = fma(c0.x, s0.x, c1.x * s1.x);
+            s0.y = fma(c0.y, s0.y, c1.y * s1.y);
         }
+        size_t o = (size_t)i * ld + c;
+        double2 out;
+        if (HAS_Z) {
+            double2 zv = ldv2(z + o);
+            out.x = fma(alpha, s0.x, beta * zv.x);
+            out.y = fma(alpha, s0.y, beta * zv.y);
+        } else {
+            out.x = alpha * s0.x;
+            out.y = alpha * s0.y;
+        }
+        stv2(y + o, out);
     }
-    if (K == 2) {
-        double2 c0 = ldg2(coef0 + c), c1 = ldg2(coef1 + c);
-        s0.x = fma(c0.x, s0.x, c1.x * s1.x);
-        s0.y = fma(c0.y, s0.y, c1.y * s1.y);
-    }
-    size_t o = (size_t)i * ld + c;
-    double2 out;
-    if (HAS_Z) {
-        double2 zv = ldv2(z + o);
-        out.x = fma(alpha, s0.x, beta * zv.x);
-        out.y = fma(alpha, s0.y, beta * zv.y);
-    } else {
-        out.x = alpha * s0.x;
-        out.y = alpha * s0.y;
-    }
-    stv2(y + o, out);
 }
 
-// y[i,t] = alpha * sum_p T[t,p] X(i, col_p) + beta * y[i,t].
-// One thread per (i, t); t fastest.  X(i, c) comes from the block for local
-// columns and from the slice-major halo buffer otherwise.
-template <bool ACC>
-__global__ void __launch_bounds__(256)
-    k_time_apply(int M, int nrows_t, const int *__restrict__ indptr,
-                 const int *__restrict__ indices, const double *__restrict__ vals,
-                 const double *__restrict__ x, int ldx, int ncols_local,
-                 const double *__restrict__ xh, double alpha, double beta,
-                 double *__restrict__ y, int ldy) {
-    unsigned k = blockIdx.x * 256u + threadIdx.x;
-    unsigned i = k / (unsigned)ldy;
-    if (i >= (unsigned)M) return;
-    unsigned t = k - i * (unsigned)ldy;
-    size_t o = (size_t)i * ldy + t;
-    if (t >= (unsigned)nrows_t) {
-        if (!ACC) y[o] = 0.0;
-        return;
-    }
-    const double *xi = x + (size_t)i * ldx;
+// One row of T against the time column of space dof i.
+__device__ __forceinline__ double time_row(int t, const int *__restrict__ indptr,
+                                           const int *__restrict__ indices,
+                                           const double *__restrict__ vals,
+                                           const double *__restrict__ xi, int ncols_local,
+                                           const double *__restrict__ xh, int M, unsigned i) {
     double s = 0.0;
     int p1 = __ldg(indptr + t + 1);
     for (int p = __ldg(indptr + t); p < p1; ++p) {
@@ -84,7 +62,40 @@ __global__ void __launch_bounds__(256)
         double xv = (c < ncols_local) ? xi[c] : __ldg(xh + (size_t)(c - ncols_local) * M + i);
         s = fma(__ldg(vals + p), xv, s);
     }
-    y[o] = ACC ? fma(alpha, s, beta * y[o]) : alpha * s;
+    return s;
+}
+
+// y[i,t] = alpha * sum_p T[t,p] X(i, col_p) + beta * y[i,t].
+// One thread per (i, pair of adjacent t); t fastest; grid-stride.  X(i, c)
+// comes from the block for local columns and from the slice-major halo buffer
+// otherwise.  Pads t >= nrows_t are written as zero (kept when accumulating).
+template <bool ACC>
+__global__ void __launch_bounds__(256)
+    k_time_apply(int M, int nrows_t, const int *__restrict__ indptr,
+                 const int *__restrict__ indices, const double *__restrict__ vals,
+                 const double *__restrict__ x, int ldx, int ncols_local,
+                 const double *__restrict__ xh, double alpha, double beta,
+                 double *__restrict__ y, int ldy) {
+    const unsigned ld2 = (unsigned)ldy / 2u;
+    const unsigned total = (unsigned)M * ld2;
+    const unsigned stride = gridDim.x * 256u;
+    for (unsigned k = blockIdx.x * 256u + threadIdx.x; k < total; k += stride) {
+        unsigned i = k / ld2;
+        int t = (int)(k - i * ld2) * 2;
+        size_t o = (size_t)i * ldy + t;
+        const double *xi = x + (size_t)i * ldx;
+        double2 out = make_double2(0.0, 0.0);
+        if (t < nrows_t)
+            out.x = alpha * time_row(t, indptr, indices, vals, xi, ncols_local, xh, M, i);
+        if (t + 1 < nrows_t)
+            out.y = alpha * time_row(t + 1, indptr, indices, vals, xi, ncols_local, xh, M, i);
+        if (ACC) {
+            double2 old = ldv2(y + o);
+            out.x = fma(beta, old.x, out.x);
+            out.y = fma(beta, old.y, out.y);
+        }
+        stv2(y + o, out);
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -118,12 +129,11 @@ int launch_space_spmm(int nrows, const int *indptr, const int *indices, int K,
     unsigned ld2 = (unsigned)ld / 2u;
     int64_t work = (int64_t)nrows * ld2;
     if (work >= (1ll << 32)) return fail(-2, "stk_space_spmm: block too large for 32-bit grid");
-    unsigned grid = blocks_for(work, 256);
     bool has_z = (beta != 0.0);
     if (has_z && z == nullptr) return fail(-1, "stk_space_spmm: beta != 0 needs z");
 #define STK_SPMM(KK, ZZ)                                                                     \
-    k_space_spmm<KK, ZZ><<<grid, 256, 0, s>>>(nrows, indptr, indices, vals0, vals1, coef0,   \
-                                              coef1, x, alpha, beta, z, y, ld, ld2)
+    k_space_spmm<KK, ZZ><<<resident_grid(k_space_spmm<KK, ZZ>, 256, work), 256, 0, s>>>(     \
+        nrows, indptr, indices, vals0, vals1, coef0, coef1, x, alpha, beta, z, y, ld, ld2)
     if (K == 1) {
         if (has_z) STK_SPMM(1, true); else STK_SPMM(1, false);
     } else {
@@ -159,15 +169,17 @@ int stk_time_apply(int M, int nrows_t, const int *indptr, const int *indices,
     if (x == y) return fail(-1, "stk_time_apply: x must not alias y");
     if (nrows_t > ldy) return fail(-1, "stk_time_apply: nrows_t exceeds the pitch of y");
     if (M == 0) return 0;
-    int64_t work = (int64_t)M * ldy;
+    if (ldy & 1) return fail(-1, "stk_time_apply: pitch of y must be even");
+    int64_t work = (int64_t)M * (ldy / 2);
     if (work >= (1ll << 32)) return fail(-2, "stk_time_apply: block too large");
-    unsigned grid = blocks_for(work, 256);
     if (beta != 0.0)
-        k_time_apply<true><<<grid, 256, 0, as_stream(stream)>>>(
-            M, nrows_t, indptr, indices, vals, x, ldx, ncols_local, xh, alpha, beta, y, ldy);
+        k_time_apply<true><<<resident_grid(k_time_apply<true>, 256, work), 256, 0,
+                             as_stream(stream)>>>(M, nrows_t, indptr, indices, vals, x, ldx,
+                                                  ncols_local, xh, alpha, beta, y, ldy);
     else
-        k_time_apply<false><<<grid, 256, 0, as_stream(stream)>>>(
-            M, nrows_t, indptr, indices, vals, x, ldx, ncols_local, xh, alpha, beta, y, ldy);
+        k_time_apply<false><<<resident_grid(k_time_apply<false>, 256, work), 256, 0,
+                              as_stream(stream)>>>(M, nrows_t, indptr, indices, vals, x, ldx,
+                                                   ncols_local, xh, alpha, beta, y, ldy);
     return check_launch("k_time_apply");
 }
 

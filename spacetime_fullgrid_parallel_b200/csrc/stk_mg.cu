@@ -36,6 +36,7 @@ struct Level {
 
 // u_i += (f_i - A_i . u) / a_ii for the rows of one wavefront
 // (multigrid.py:89-97: whole row including the diagonal, then the update).
+// Grid-stride over (row, double2 column) items with a resident grid.
 template <int K>
 __global__ void __launch_bounds__(256)
     k_gs_phase(const int *__restrict__ rows, int nrows, const int *__restrict__ indptr,
@@ -44,41 +45,32 @@ __global__ void __launch_bounds__(256)
                const double *__restrict__ d1, const double *__restrict__ coef0,
                const double *__restrict__ coef1, const double *__restrict__ f, double *u, int ld,
                unsigned ld2) {
-    unsigned k = blockIdx.x * 256u + threadIdx.x;
-    unsigned r = k / ld2;
-    if (r >= (unsigned)nrows) return;
-    unsigned c = (k - r * ld2) * 2u;
-    int i = __ldg(rows + r);
-    int p0 = __ldg(indptr + i), p1 = __ldg(indptr + i + 1);
-    double2 s0 = make_double2(0.0, 0.0), s1 = make_double2(0.0, 0.0);
-    for (int p = p0; p < p1; ++p) {
-        int j = __ldg(indices + p);
-        double2 uv = ldv2(u + (size_t)j * ld + c);
-        double a0 = __ldg(v0 + p);
-        s0.x = fma(a0, uv.x, s0.x);
-        s0.y = fma(a0, uv.y, s0.y);
+    const unsigned total = (unsigned)nrows * ld2;
+    const unsigned stride = gridDim.x * 256u;
+    for (unsigned k = blockIdx.x * 256u + threadIdx.x; k < total; k += stride) {
+        unsigned r = k / ld2;
+        unsigned c = (k - r * ld2) * 2u;
+        int i = __ldg(rows + r);
+        int p0 = __ldg(indptr + i), p1 = __ldg(indptr + i + 1);
+        double2 s0 = make_double2(0.0, 0.0), s1 = make_double2(0.0, 0.0);
+        row_product<K, 0>(p0, p1, indices, v0, v1, u, ld, c, s0, s1);
+        double2 diag;
         if (K == 2) {
-            double a1 = __ldg(v1 + p);
-            s1.x = fma(a1, uv.x, s1.x);
-            s1.y = fma(a1, uv.y, s1.y);
+            double2 c0 = ldg2(coef0 + c), c1 = ldg2(coef1 + c);
+            s0.x = fma(c0.x, s0.x, c1.x * s1.x);
+            s0.y = fma(c0.y, s0.y, c1.y * s1.y);
+            double e0 = __ldg(d0 + i), e1 = __ldg(d1 + i);
+            diag.x = fma(c0.x, e0, c1.x * e1);
+            diag.y = fma(c0.y, e0, c1.y * e1);
+        } else {
+            diag.x = diag.y = __ldg(d0 + i);
         }
+        size_t o = (size_t)i * ld + c;
+        double2 fv = ldv2(f + o), uo = ldv2(u + o);
+        uo.x += (fv.x - s0.x) / diag.x;
+        uo.y += (fv.y - s0.y) / diag.y;
+        stv2(u + o, uo);
     }
-    double2 diag;
-    if (K == 2) {
-        double2 c0 = ldg2(coef0 + c), c1 = ldg2(coef1 + c);
-        s0.x = fma(c0.x, s0.x, c1.x * s1.x);
-        s0.y = fma(c0.y, s0.y, c1.y * s1.y);
-        double e0 = __ldg(d0 + i), e1 = __ldg(d1 + i);
-        diag.x = fma(c0.x, e0, c1.x * e1);
-        diag.y = fma(c0.y, e0, c1.y * e1);
-    } else {
-        diag.x = diag.y = __ldg(d0 + i);
-    }
-    size_t o = (size_t)i * ld + c;
-    double2 fv = ldv2(f + o), uo = ldv2(u + o);
-    uo.x += (fv.x - s0.x) / diag.x;
-    uo.y += (fv.y - s0.y) / diag.y;
-    stv2(u + o, uo);
 }
 
 // u[i,t] = sum_j inv[g(t)][i,j] f[j,t]   (multigrid.py:161-170, exact solve).
@@ -114,13 +106,15 @@ static int smooth(const stk_mg *mg, int l, int nsweeps, bool backward, const dou
             int ph = backward ? nph - 1 - q : q;
             int r0 = lv.phase_ptr[ph], nr = lv.phase_ptr[ph + 1] - r0;
             if (nr == 0) continue;
-            unsigned grid = blocks_for((int64_t)nr * ld2, 256);
+            if ((int64_t)nr * ld2 >= (1ll << 32)) return fail(-2, "stk_mg: block too large");
             if (mg->K == 2)
-                k_gs_phase<2><<<grid, 256, 0, s>>>(lv.sched + r0, nr, lv.indptr, lv.indices, lv.v0,
-                                                   lv.v1, lv.d0, lv.d1, c0, c1, f, u, ld, ld2);
+                k_gs_phase<2><<<resident_grid(k_gs_phase<2>, 256, (int64_t)nr * ld2), 256, 0, s>>>(
+                    lv.sched + r0, nr, lv.indptr, lv.indices, lv.v0, lv.v1, lv.d0, lv.d1, c0, c1,
+                    f, u, ld, ld2);
             else
-                k_gs_phase<1><<<grid, 256, 0, s>>>(lv.sched + r0, nr, lv.indptr, lv.indices, lv.v0,
-                                                   lv.v1, lv.d0, lv.d1, c0, c1, f, u, ld, ld2);
+                k_gs_phase<1><<<resident_grid(k_gs_phase<1>, 256, (int64_t)nr * ld2), 256, 0, s>>>(
+                    lv.sched + r0, nr, lv.indptr, lv.indices, lv.v0, lv.v1, lv.d0, lv.d1, c0, c1,
+                    f, u, ld, ld2);
             STK_TRY(check_launch("k_gs_phase"));
         }
     }

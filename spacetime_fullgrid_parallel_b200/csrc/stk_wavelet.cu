@@ -74,8 +74,6 @@ __global__ void k_wavelet_lift(int M, int J, double *__restrict__ x, int ld) {
     }
 }
 
-int sm_count();
-
 }  // namespace stk
 
 using namespace stk;

@@ -37,7 +37,10 @@ struct Level {
 // u_i += (f_i - A_i . u) / a_ii for the rows of one wavefront
 // (multigrid.py:89-97: whole row including the diagonal, then the update).
 // Grid-stride over (row, double2 column) items with a resident grid.
-template <int K>
+// FIRST: first forward sweep from a zero initial guess = forward substitution
+// with the lower triangle, u_i = (f_i - sum_{j<i} a_ij u_j) / a_ii: entries
+// j >= i multiply zeros and are skipped, u is write-only (no memset needed).
+template <int K, bool FIRST>
 __global__ void __launch_bounds__(256)
     k_gs_phase(const int *__restrict__ rows, int nrows, const int *__restrict__ indptr,
                const int *__restrict__ indices, const double *__restrict__ v0,
@@ -53,7 +56,23 @@ __global__ void __launch_bounds__(256)
         int i = __ldg(rows + r);
         int p0 = __ldg(indptr + i), p1 = __ldg(indptr + i + 1);
         double2 s0 = make_double2(0.0, 0.0), s1 = make_double2(0.0, 0.0);
-        row_product<K, 0>(p0, p1, indices, v0, v1, u, ld, c, s0, s1);
+        if (FIRST) {  // column indices are sorted: the lower triangle comes first
+            for (int p = p0; p < p1; ++p) {
+                int jj = __ldg(indices + p);
+                if (jj >= i) break;
+                double2 xx = ldv2(u + (size_t)jj * ld + c);
+                double b0 = __ldg(v0 + p);
+                s0.x = fma(b0, xx.x, s0.x);
+                s0.y = fma(b0, xx.y, s0.y);
+                if (K == 2) {
+                    double b1 = __ldg(v1 + p);
+                    s1.x = fma(b1, xx.x, s1.x);
+                    s1.y = fma(b1, xx.y, s1.y);
+                }
+            }
+        } else {
+            row_product<K, 0>(p0, p1, indices, v0, v1, u, ld, c, s0, s1);
+        }
         double2 diag;
         if (K == 2) {
             double2 c0 = ldg2(coef0 + c), c1 = ldg2(coef1 + c);
@@ -66,7 +85,8 @@ __global__ void __launch_bounds__(256)
             diag.x = diag.y = __ldg(d0 + i);
         }
         size_t o = (size_t)i * ld + c;
-        double2 fv = ldv2(f + o), uo = ldv2(u + o);
+        double2 fv = ldv2(f + o), uo = make_double2(0.0, 0.0);
+        if (!FIRST) uo = ldv2(u + o);
         uo.x += (fv.x - s0.x) / diag.x;
         uo.y += (fv.y - s0.y) / diag.y;
         stv2(u + o, uo);
@@ -97,7 +117,8 @@ struct stk_mg {
 };
 
 static int smooth(const stk_mg *mg, int l, int nsweeps, bool backward, const double *c0,
-                  const double *c1, const double *f, double *u, int ld, cudaStream_t s) {
+                  const double *c1, const double *f, double *u, int ld, cudaStream_t s,
+                  bool zero_guess = false) {
     const Level &lv = mg->L[l];
     const int nph = (int)lv.phase_ptr.size() - 1;
     const unsigned ld2 = (unsigned)ld / 2u;
@@ -107,14 +128,17 @@ static int smooth(const stk_mg *mg, int l, int nsweeps, bool backward, const dou
             int r0 = lv.phase_ptr[ph], nr = lv.phase_ptr[ph + 1] - r0;
             if (nr == 0) continue;
             if ((int64_t)nr * ld2 >= (1ll << 32)) return fail(-2, "stk_mg: block too large");
-            if (mg->K == 2)
-                k_gs_phase<2><<<resident_grid(k_gs_phase<2>, 256, (int64_t)nr * ld2), 256, 0, s>>>(
-                    lv.sched + r0, nr, lv.indptr, lv.indices, lv.v0, lv.v1, lv.d0, lv.d1, c0, c1,
-                    f, u, ld, ld2);
-            else
-                k_gs_phase<1><<<resident_grid(k_gs_phase<1>, 256, (int64_t)nr * ld2), 256, 0, s>>>(
-                    lv.sched + r0, nr, lv.indptr, lv.indices, lv.v0, lv.v1, lv.d0, lv.d1, c0, c1,
-                    f, u, ld, ld2);
+            const bool first = zero_guess && sw == 0 && !backward;
+#define STK_GS(KK, FF)                                                                        \
+    k_gs_phase<KK, FF><<<resident_grid(k_gs_phase<KK, FF>, 256, (int64_t)nr * ld2), 256, 0, s>>>( \
+        lv.sched + r0, nr, lv.indptr, lv.indices, lv.v0, lv.v1, lv.d0, lv.d1, c0, c1, f, u, ld,  \
+        ld2)
+            if (mg->K == 2) {
+                if (first) STK_GS(2, true); else STK_GS(2, false);
+            } else {
+                if (first) STK_GS(1, true); else STK_GS(1, false);
+            }
+#undef STK_GS
             STK_TRY(check_launch("k_gs_phase"));
         }
     }
@@ -133,23 +157,27 @@ static int coarse_solve(const stk_mg *mg, const double *inv, const int *group, c
     return check_launch("k_coarse_solve");
 }
 
-// MGM(j, u_j, f_j) of multigrid.py:168-182.
+// MGM(j, u_j, f_j) of multigrid.py:168-182.  `zero_guess`: u holds no data yet
+// and stands for u = 0 (the reference passes np.zeros, multigrid.py:176,187).
 static int cycle(const stk_mg *mg, int l, const double *c0, const double *c1, const double *inv,
                  const int *group, const double *f, double *u, int ld, Workspace &ws,
-                 cudaStream_t s) {
+                 cudaStream_t s, bool zero_guess) {
     if (l == 0) return coarse_solve(mg, inv, group, f, u, ld, s);
     const Level &lv = mg->L[l];
     const Level &lc = mg->L[l - 1];
-    STK_TRY(smooth(mg, l, mg->nu, false, c0, c1, f, u, ld, s));
-    // res = A u - f
+    if (zero_guess && mg->nu == 0)
+        STK_TRY(check(cudaMemsetAsync(u, 0, sizeof(double) * (size_t)lv.n * ld, s),
+                      "stk_mg: memset"));
+    STK_TRY(smooth(mg, l, mg->nu, false, c0, c1, f, u, ld, s, zero_guess));
+    // res = A u - f, f_c = R res (multigrid.py:174).  A fused kernel that
+    // recomputes the fine residuals per coarse row was measured 2.6x slower
+    // (6 block passes of DRAM reads instead of ~3): the residual block costs
+    // less than the lost locality.
     STK_TRY(launch_space_spmm(lv.n, lv.indptr, lv.indices, mg->K, lv.v0, lv.v1, c0, c1, u, 1.0,
                               -1.0, f, ws.res, ld, s));
-    // f_c = R res
     STK_TRY(launch_space_spmm(lc.n, lv.r_indptr, lv.r_indices, 1, lv.r_vals, nullptr, nullptr,
                               nullptr, ws.res, 1.0, 0.0, nullptr, ws.f[l - 1], ld, s));
-    STK_TRY(check(cudaMemsetAsync(ws.u[l - 1], 0, sizeof(double) * (size_t)lc.n * ld, s),
-                  "stk_mg: memset"));
-    STK_TRY(cycle(mg, l - 1, c0, c1, inv, group, ws.f[l - 1], ws.u[l - 1], ld, ws, s));
+    STK_TRY(cycle(mg, l - 1, c0, c1, inv, group, ws.f[l - 1], ws.u[l - 1], ld, ws, s, true));
     // u -= P u_c
     STK_TRY(launch_space_spmm(lv.n, lv.p_indptr, lv.p_indices, 1, lv.p_vals, nullptr, nullptr,
                               nullptr, ws.u[l - 1], -1.0, 1.0, u, u, ld, s));
@@ -237,10 +265,11 @@ int stk_mg_apply(stk_mg *mg, const double *coef0, const double *coef1, const dou
         q += (size_t)mg->L[l].n * ld;
     }
     ws.res = q;
-    STK_TRY(check(cudaMemsetAsync(x, 0, sizeof(double) * (size_t)mg->L[top].n * ld, s),
-                  "stk_mg_apply: memset"));
+    if (mg->vcycles == 0)
+        STK_TRY(check(cudaMemsetAsync(x, 0, sizeof(double) * (size_t)mg->L[top].n * ld, s),
+                      "stk_mg_apply: memset"));
     for (int v = 0; v < mg->vcycles; ++v)
-        STK_TRY(cycle(mg, top, coef0, coef1, coarse_inv, coarse_group, b, x, ld, ws, s));
+        STK_TRY(cycle(mg, top, coef0, coef1, coarse_inv, coarse_group, b, x, ld, ws, s, v == 0));
     return 0;
 }
 

@@ -52,6 +52,10 @@ def main():
         print('%-34s %9.3f ms  %8.1f GB/s (alg, %4.0f B/dof)  %.3f of peak' %
               (name, ms, gbs, bytes_per_dof, gbs / peak), flush=True)
 
+    if args.only == 'mg':
+        timeit('MG K_x apply (2 V(3,3))', lambda: heq.Kinv_x.apply_block(x.data, y.data), 523,
+               reps=1)
+        return
     u = torch.zeros_like(x.data)
     for var in os.environ.get('GS_VARIANTS', '').split():
         os.environ['STK_GS_VARIANT'] = var

@@ -240,7 +240,15 @@ class SquareProblem:
         u0 = self.hierarchy.nodal_values(
             lambda x, y: np.sin(np.pi * x) * np.sin(np.pi * y))
         self.u0_x = self.M_x @ u0
-        # heateq_mpi.py:97-98
-        self.Cinv_j = [
-            2**j * self.M_x + alpha * self.A_x for j in range(J_time + 1)
-        ]
+        self._Cinv_j = None
+
+    @property
+    def Cinv_j(self):
+        """2^j M_x + alpha A_x, j = 0..J_time (heateq_mpi.py:97-98); built on
+        first use -- the device path works from M_x and A_x directly."""
+        if self._Cinv_j is None:
+            self._Cinv_j = [
+                2**j * self.M_x + self.alpha * self.A_x
+                for j in range(self.J_time + 1)
+            ]
+        return self._Cinv_j

@@ -10,6 +10,9 @@
 // The matrix of slice t is c0[t]*A0 + c1[t]*A1 on a shared pattern (K = 2),
 // which serves K_x = MG(A_x) and every C_j = MG(2^j M_x + alpha A_x) of
 // heateq_mpi.py:143-153 with ONE hierarchy and one launch sequence.
+#include <stdlib.h>
+
+#include <unordered_map>
 #include <vector>
 
 #include "stk_common.cuh"
@@ -111,9 +114,39 @@ __global__ void __launch_bounds__(256)
 
 using namespace stk;
 
+// One captured V-cycle sequence: the launch arguments are baked in, so a
+// graph is keyed by every pointer it was captured with.
+struct GraphKey {
+    const void *p[7];
+    int ld;
+    bool operator==(const GraphKey &o) const {
+        for (int k = 0; k < 7; ++k)
+            if (p[k] != o.p[k]) return false;
+        return ld == o.ld;
+    }
+};
+struct GraphKeyHash {
+    size_t operator()(const GraphKey &k) const {
+        size_t h = (size_t)k.ld * 1000003u;
+        for (int i = 0; i < 7; ++i) h = h * 1099511628211ull ^ (size_t)k.p[i];
+        return h;
+    }
+};
+struct GraphEntry {
+    cudaGraphExec_t exec = nullptr;  // null: key seen once, not captured yet
+    int64_t launches = 0;
+};
+
 struct stk_mg {
     int nlevels, nu, vcycles, K;
     std::vector<Level> L;
+    std::unordered_map<GraphKey, GraphEntry, GraphKeyHash> graphs;
+    cudaStream_t capture_stream = nullptr;
+    ~stk_mg() {
+        for (auto &kv : graphs)
+            if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+        if (capture_stream) cudaStreamDestroy(capture_stream);
+    }
 };
 
 static int smooth(const stk_mg *mg, int l, int nsweeps, bool backward, const double *c0,
@@ -265,11 +298,67 @@ int stk_mg_apply(stk_mg *mg, const double *coef0, const double *coef1, const dou
         q += (size_t)mg->L[l].n * ld;
     }
     ws.res = q;
-    if (mg->vcycles == 0)
-        STK_TRY(check(cudaMemsetAsync(x, 0, sizeof(double) * (size_t)mg->L[top].n * ld, s),
-                      "stk_mg_apply: memset"));
-    for (int v = 0; v < mg->vcycles; ++v)
-        STK_TRY(cycle(mg, top, coef0, coef1, coarse_inv, coarse_group, b, x, ld, ws, s, v == 0));
+    auto run = [&](cudaStream_t st) -> int {
+        if (mg->vcycles == 0)
+            STK_TRY(check(cudaMemsetAsync(x, 0, sizeof(double) * (size_t)mg->L[top].n * ld, st),
+                          "stk_mg_apply: memset"));
+        for (int v = 0; v < mg->vcycles; ++v)
+            STK_TRY(cycle(mg, top, coef0, coef1, coarse_inv, coarse_group, b, x, ld, ws, st,
+                          v == 0));
+        return 0;
+    };
+    // The apply is hundreds of launches, most of them on coarse levels where a
+    // launch costs more than the kernel.  The second time the same buffers
+    // come back (torch's caching allocator recycles addresses in a Krylov
+    // loop) the sequence is captured into a CUDA graph; from then on it is
+    // one graph launch.  STK_MG_GRAPH=0 disables this.
+    static const bool use_graphs = [] {
+        const char *e = getenv("STK_MG_GRAPH");
+        return !(e && e[0] == '0');
+    }();
+    if (!use_graphs) return run(s);
+    GraphKey key{{coef0, coef1, coarse_inv, coarse_group, b, x, wsbuf}, ld};
+    auto it = mg->graphs.find(key);
+    if (it == mg->graphs.end()) {
+        if (mg->graphs.size() >= 64) {  // buffers are not recurring: start over
+            for (auto &kv : mg->graphs)
+                if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+            mg->graphs.clear();
+        }
+        mg->graphs.emplace(key, GraphEntry());
+        return run(s);
+    }
+    if (!it->second.exec) {
+        if (!mg->capture_stream)
+            STK_TRY(check(cudaStreamCreateWithFlags(&mg->capture_stream, cudaStreamNonBlocking),
+                          "stk_mg_apply: capture stream"));
+        cudaGraph_t graph = nullptr;
+        int64_t before = g_launches;
+        STK_TRY(check(cudaStreamBeginCapture(mg->capture_stream, cudaStreamCaptureModeThreadLocal),
+                      "stk_mg_apply: begin capture"));
+        int rc = run(mg->capture_stream);
+        cudaError_t e = cudaStreamEndCapture(mg->capture_stream, &graph);
+        int64_t captured = g_launches - before;
+        g_launches = before;
+        if (rc != 0 || e != cudaSuccess || !graph) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            mg->graphs.erase(it);
+            return run(s);  // capture unavailable: plain launches
+        }
+        cudaGraphExec_t exec = nullptr;
+        e = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            mg->graphs.erase(it);
+            return run(s);
+        }
+        it->second.exec = exec;
+        it->second.launches = captured;
+    }
+    STK_TRY(check(cudaGraphLaunch(it->second.exec, s), "stk_mg_apply: graph launch"));
+    g_launches += it->second.launches;
     return 0;
 }
 

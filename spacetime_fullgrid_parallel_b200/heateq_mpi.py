@@ -182,8 +182,8 @@ class HeatEquationMPI:
 
         # ---- right-hand side (heateq_mpi.py:188-191) ----
         self.rhs = KronVectorMPI(d)
-        self.rhs.X_loc[:] = np.kron(self.u0_t[self.rhs.t_begin:self.rhs.t_end],
-                                    self.u0_x).reshape(-1, self.M)
+        self.rhs.set_kron(self.u0_t[self.rhs.t_begin:self.rhs.t_end],
+                          self.u0_x)
         self.setup_time = Wtime() - start_time
         self.mem_after_mpi = mem()
 

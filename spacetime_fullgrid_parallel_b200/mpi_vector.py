@@ -180,6 +180,18 @@ class KronVectorMPI:
                                             stream()))
         return host
 
+    def set_kron(self, u_t_loc, u_x):
+        """self = u_t_loc (x) u_x, i.e. X_loc = np.kron(u_t_loc, u_x) reshaped
+        (heateq_mpi.py:189-191), formed on the device from the two factors."""
+        assert len(u_t_loc) == self.n_loc and len(u_x) == self.M
+        self._invalidate()
+        dev = self.data.device
+        ut = torch.zeros(self.ld, dtype=torch.float64, device=dev)
+        ut[:self.n_loc] = torch.as_tensor(np.asarray(u_t_loc, dtype=np.float64))
+        ux = torch.as_tensor(np.asarray(u_x, dtype=np.float64)).to(dev)
+        torch.outer(ux, ut, out=self.data)
+        return self
+
     def copy(self):
         return KronVectorMPI(self.dofs_distr, _data=self.data.clone())
 

@@ -62,6 +62,10 @@ class TimeOpPlan:
         self.adj_local = lt[:n].tocsr()
         self.adj_halo = lt[n:].tocsr()
         self._dev = None
+        # plans that move the same slices share one exchange per vector state
+        self._key = ('halo', self.halo_cols.tobytes(),
+                     tuple(sorted((p, v.tobytes())
+                                  for p, v in self.send_to.items())))
 
     # -- device execution --------------------------------------------------
     def _device_arrays(self, device):
@@ -92,8 +96,7 @@ class TimeOpPlan:
         cached on the vector until it is written (mpi_vector.py:143-145)."""
         import torch
         from ._lib import check, lib, ptr, stream
-        key = ('halo', self.halo_cols.tobytes(),
-               tuple(sorted((p, v.tobytes()) for p, v in self.send_to.items())))
+        key = self._key
         if key in vec._halo:
             if callback is not None:
                 callback()

@@ -101,12 +101,15 @@ int stk_space_spmm(int nrows, const int *indptr, const int *indices, int K,
  *   t in [0, nrows_t); pads t in [nrows_t, ldy) are written as zero when
  *   beta == 0.
  * X(i,c) = x[i*ldx + c] for c < ncols_local, else the halo slice
- * xh[(c-ncols_local)*M + i] (slice-major, as received from a neighbour rank,
- * mpi_vector.py:140-203).  y must not alias x. */
-int stk_time_apply(int M, int nrows_t, const int *indptr, const int *indices,
-                   const double *vals, const double *x, int ldx,
-                   int ncols_local, const double *xh, double alpha,
-                   double beta, double *y, int ldy, void *stream);
+ * xh[(c-ncols_local)*M + i] (slice-major, n_halo slices as received from
+ * neighbour ranks, mpi_vector.py:140-203).  nnz = indptr[nrows_t].  Matrices
+ * with many nonzeros per row (the multi-level wavelet transform) are staged in
+ * shared memory together with a panel of time columns.  y must not alias x. */
+int stk_time_apply(int M, int nrows_t, int nnz, const int *indptr,
+                   const int *indices, const double *vals, const double *x,
+                   int ldx, int ncols_local, const double *xh, int n_halo,
+                   double alpha, double beta, double *y, int ldy,
+                   void *stream);
 /* out[h*M + i] = x[i*ld + tidx[h]]   (pack time slices for a send). */
 int stk_pack_slices(const double *x, int ld, int M, const int *tidx, int n,
                     double *out, void *stream);

@@ -33,8 +33,8 @@ SIGNATURES = {
         _int, _vp
     ]),
     'stk_time_apply': (_int, [
-        _int, _int, _vp, _vp, _vp, _vp, _int, _int, _vp, _dbl, _dbl, _vp,
-        _int, _vp
+        _int, _int, _int, _vp, _vp, _vp, _vp, _int, _int, _vp, _int, _dbl,
+        _dbl, _vp, _int, _vp
     ]),
     'stk_pack_slices': (_int, [_vp, _int, _int, _vp, _int, _vp, _vp]),
     'stk_unpack_slices': (_int,

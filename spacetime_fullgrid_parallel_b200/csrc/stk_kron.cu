@@ -98,6 +98,76 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// Shared-memory form for time matrices with many nonzeros per row (the
+// multi-level wavelet transform has ~2J+1): the whole CSR matrix and a panel
+// of RB time columns (local slices + halo slices) are staged in shared memory,
+// so the ~19 loads per output hit shared memory instead of L1/L2, and the
+// panel is read from HBM once with coalesced loads.  Persistent CTAs walk the
+// panels.  Shared layout: vals[nnz] | xs[RB][W] | indptr[nrows_t+1] | idx[nnz].
+template <bool ACC>
+__global__ void __launch_bounds__(256)
+    k_time_apply_smem(int M, int nrows_t, int nnz, const int *__restrict__ indptr,
+                      const int *__restrict__ indices, const double *__restrict__ vals,
+                      const double *__restrict__ x, int ldx, int ncols_local,
+                      const double *__restrict__ xh, int n_halo, double alpha, double beta,
+                      double *__restrict__ y, int ldy, int RB, int W) {
+    extern __shared__ double smem_d[];
+    double *s_val = smem_d;
+    double *xs = s_val + nnz;
+    int *s_ptr = reinterpret_cast<int *>(xs + (size_t)RB * W);
+    int *s_idx = s_ptr + nrows_t + 1;
+    for (int k = threadIdx.x; k < nnz; k += 256) {
+        s_val[k] = __ldg(vals + k);
+        s_idx[k] = __ldg(indices + k);
+    }
+    for (int k = threadIdx.x; k <= nrows_t; k += 256) s_ptr[k] = __ldg(indptr + k);
+    const int ntiles = (M + RB - 1) / RB;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int i0 = tile * RB;
+        const int rb = min(RB, M - i0);
+        __syncthreads();  // matrix staged / previous panel consumed
+        for (int e = threadIdx.x; e < rb * ncols_local; e += 256) {
+            int r = e / ncols_local, c = e - r * ncols_local;
+            xs[r * W + c] = x[(size_t)(i0 + r) * ldx + c];
+        }
+        for (int e = threadIdx.x; e < rb * n_halo; e += 256) {
+            int h = e / rb, r = e - h * rb;
+            xs[r * W + ncols_local + h] = __ldg(xh + (size_t)h * M + i0 + r);
+        }
+        __syncthreads();
+        // each thread: one time row t for RR panel columns (the matrix entry
+        // is read once from shared memory and reused RR times)
+        constexpr int RR = 4;
+        const int ngroups = (rb + RR - 1) / RR;
+        for (int e = threadIdx.x; e < ngroups * ldy; e += 256) {
+            int g = e / ldy, t = e - g * ldy;
+            int r0 = g * RR;
+            double acc[RR];
+#pragma unroll
+            for (int k = 0; k < RR; ++k) acc[k] = 0.0;
+            if (t < nrows_t) {
+                const double *xr = xs + r0 * W;
+                for (int p = s_ptr[t]; p < s_ptr[t + 1]; ++p) {
+                    double v = s_val[p];
+                    int c = s_idx[p];
+#pragma unroll
+                    for (int k = 0; k < RR; ++k) acc[k] = fma(v, xr[k * W + c], acc[k]);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < RR; ++k) {
+                if (r0 + k >= rb) break;
+                size_t o = (size_t)(i0 + r0 + k) * ldy + t;
+                if (t >= nrows_t) {
+                    if (!ACC) y[o] = 0.0;
+                } else {
+                    y[o] = ACC ? fma(alpha, acc[k], beta * y[o]) : alpha * acc[k];
+                }
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256)
     k_pack_slices(const double *__restrict__ x, int ld, int M, const int *__restrict__ tidx,
                   int n, double *__restrict__ out) {
@@ -162,9 +232,9 @@ int stk_space_spmm(int nrows, const int *indptr, const int *indices, int K, cons
                              beta, z, y, ld, as_stream(stream));
 }
 
-int stk_time_apply(int M, int nrows_t, const int *indptr, const int *indices,
+int stk_time_apply(int M, int nrows_t, int nnz, const int *indptr, const int *indices,
                    const double *vals, const double *x, int ldx, int ncols_local,
-                   const double *xh, double alpha, double beta, double *y, int ldy,
+                   const double *xh, int n_halo, double alpha, double beta, double *y, int ldy,
                    void *stream) {
     if (x == y) return fail(-1, "stk_time_apply: x must not alias y");
     if (nrows_t > ldy) return fail(-1, "stk_time_apply: nrows_t exceeds the pitch of y");
@@ -172,14 +242,45 @@ int stk_time_apply(int M, int nrows_t, const int *indptr, const int *indices,
     if (ldy & 1) return fail(-1, "stk_time_apply: pitch of y must be even");
     int64_t work = (int64_t)M * (ldy / 2);
     if (work >= (1ll << 32)) return fail(-2, "stk_time_apply: block too large");
+    cudaStream_t s = as_stream(stream);
+    // Dense-ish time matrices (> 4 nonzeros per row on average) go through the
+    // shared-memory kernel when the matrix and a panel of >= 8 columns fit.
+    const int W = (ncols_local + n_halo) | 1;  // odd pitch: conflict-free column walks
+    const size_t mat_bytes = (size_t)nnz * 12 + (size_t)(nrows_t + 1) * 4 + 16;
+    const size_t budget = 72 * 1024;
+    if (nnz > 4 * (int64_t)nrows_t && mat_bytes + (size_t)8 * W * 8 <= budget) {
+        int RB = (int)((budget - mat_bytes) / ((size_t)W * 8));
+        if (RB > 64) RB = 64;
+        RB &= ~3;  // panels are consumed four columns at a time
+        size_t smem = mat_bytes + (size_t)RB * W * 8;
+        int64_t ntiles = ((int64_t)M + RB - 1) / RB;
+        if (beta != 0.0) {
+            STK_TRY(check(cudaFuncSetAttribute(k_time_apply_smem<true>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)budget),
+                          "stk_time_apply: smem attribute"));
+            int64_t cap = (int64_t)sm_count() * 3;
+            k_time_apply_smem<true><<<(unsigned)(ntiles < cap ? ntiles : cap), 256, smem, s>>>(
+                M, nrows_t, nnz, indptr, indices, vals, x, ldx, ncols_local, xh, n_halo, alpha,
+                beta, y, ldy, RB, W);
+        } else {
+            STK_TRY(check(cudaFuncSetAttribute(k_time_apply_smem<false>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)budget),
+                          "stk_time_apply: smem attribute"));
+            int64_t cap = (int64_t)sm_count() * 3;
+            k_time_apply_smem<false><<<(unsigned)(ntiles < cap ? ntiles : cap), 256, smem, s>>>(
+                M, nrows_t, nnz, indptr, indices, vals, x, ldx, ncols_local, xh, n_halo, alpha,
+                beta, y, ldy, RB, W);
+        }
+        return check_launch("k_time_apply_smem");
+    }
     if (beta != 0.0)
-        k_time_apply<true><<<resident_grid(k_time_apply<true>, 256, work), 256, 0,
-                             as_stream(stream)>>>(M, nrows_t, indptr, indices, vals, x, ldx,
-                                                  ncols_local, xh, alpha, beta, y, ldy);
+        k_time_apply<true><<<resident_grid(k_time_apply<true>, 256, work), 256, 0, s>>>(
+            M, nrows_t, indptr, indices, vals, x, ldx, ncols_local, xh, alpha, beta, y, ldy);
     else
-        k_time_apply<false><<<resident_grid(k_time_apply<false>, 256, work), 256, 0,
-                              as_stream(stream)>>>(M, nrows_t, indptr, indices, vals, x, ldx,
-                                                   ncols_local, xh, alpha, beta, y, ldy);
+        k_time_apply<false><<<resident_grid(k_time_apply<false>, 256, work), 256, 0, s>>>(
+            M, nrows_t, indptr, indices, vals, x, ldx, ncols_local, xh, alpha, beta, y, ldy);
     return check_launch("k_time_apply");
 }
 

@@ -241,10 +241,11 @@ class MatKronIdentityMPI(LinearOperatorMPI):
         sblock = self.pplan.forward(vec_in.data, vec_in.n_loc, vec_in.ld)
         self.time_communication += Wtime() - start
         res = torch.empty_like(sblock)
-        check(lib().stk_time_apply(sblock.shape[0], self.N, ptr(indptr),
-                                   ptr(indices), ptr(vals), ptr(sblock),
-                                   sblock.shape[1], self.N, None, 1.0, 0.0,
-                                   ptr(res), res.shape[1], stream()))
+        check(lib().stk_time_apply(sblock.shape[0], self.N, self.T.nnz,
+                                   ptr(indptr), ptr(indices), ptr(vals),
+                                   ptr(sblock), sblock.shape[1], self.N, None,
+                                   0, 1.0, 0.0, ptr(res), res.shape[1],
+                                   stream()))
         start = Wtime()
         out = self.pplan.backward(res, vec_in.n_loc, vec_in.ld)
         self.time_communication += Wtime() - start

@@ -129,11 +129,12 @@ class TimeOpPlan:
         dev = self._device_arrays(vec_in.data.device)
         halo = self.fetch(vec_in) if self.n_halo else None
         indptr, indices, vals = dev['local']
-        check(lib().stk_time_apply(vec_in.M, self.n_loc, ptr(indptr),
-                                   ptr(indices), ptr(vals), ptr(vec_in.data),
-                                   vec_in.ld, self.n_loc, ptr(halo),
-                                   float(alpha), float(beta), ptr(out_block),
-                                   vec_in.ld, stream()))
+        check(lib().stk_time_apply(vec_in.M, self.n_loc, self.local.nnz,
+                                   ptr(indptr), ptr(indices), ptr(vals),
+                                   ptr(vec_in.data), vec_in.ld, self.n_loc,
+                                   ptr(halo), self.n_halo, float(alpha),
+                                   float(beta), ptr(out_block), vec_in.ld,
+                                   stream()))
 
     def apply_adjoint(self, vec_in, vec_out):
         """vec_out = (T^T (x) I) vec_in: local partial sums, then the partial
@@ -146,10 +147,10 @@ class TimeOpPlan:
         M, n = vec_in.M, self.n_loc
         vec_out._invalidate()
         indptr, indices, vals = dev['adj_local']
-        check(lib().stk_time_apply(M, n, ptr(indptr), ptr(indices), ptr(vals),
-                                   ptr(vec_in.data), vec_in.ld, n, None, 1.0,
-                                   0.0, ptr(vec_out.data), vec_out.ld,
-                                   stream()))
+        check(lib().stk_time_apply(M, n, self.adj_local.nnz, ptr(indptr),
+                                   ptr(indices), ptr(vals), ptr(vec_in.data),
+                                   vec_in.ld, n, None, 0, 1.0, 0.0,
+                                   ptr(vec_out.data), vec_out.ld, stream()))
         if not self.n_halo and not self.send_to:
             return
         sends, recvs = {}, {}
@@ -158,9 +159,9 @@ class TimeOpPlan:
             part = torch.empty((M, ldh), dtype=torch.float64,
                                device=vec_in.data.device)
             indptr, indices, vals = dev['adj_halo']
-            check(lib().stk_time_apply(M, self.n_halo, ptr(indptr),
-                                       ptr(indices), ptr(vals),
-                                       ptr(vec_in.data), vec_in.ld, n, None,
+            check(lib().stk_time_apply(M, self.n_halo, self.adj_halo.nnz,
+                                       ptr(indptr), ptr(indices), ptr(vals),
+                                       ptr(vec_in.data), vec_in.ld, n, None, 0,
                                        1.0, 0.0, ptr(part), ldh, stream()))
             packed = torch.empty((self.n_halo, M), dtype=torch.float64,
                                  device=vec_in.data.device)

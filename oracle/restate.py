@@ -250,8 +250,12 @@ class HeatEqOracle:
         P_mats = p.hierarchy.P_mats
         self.J = p.J_time
         self.interleaved = interleaved
-        self.K = MultiGridOracle(p.A_x, P_mats, smoothsteps, vcycles, threads)
-        self.C = [MultiGridOracle(m, P_mats, smoothsteps, vcycles, threads)
+        # `threads` > 1: the time slices are split into slabs, one per host
+        # thread, exactly like the reference's MPI ranks (mpi_vector.py:18-31);
+        # the C kernels and SciPy's sparse products release the GIL.
+        self.threads = threads
+        self.K = MultiGridOracle(p.A_x, P_mats, smoothsteps, vcycles)
+        self.C = [MultiGridOracle(m, P_mats, smoothsteps, vcycles)
                   for m in p.Cinv_j]
         self.levels = wavelet_levels(self.J, interleaved)
         K, Mx, Ax = self.K, p.M_x, p.A_x
@@ -270,12 +274,32 @@ class HeatEqOracle:
     def WT(self, X):
         return wavelet_analysis(X, self.J, self.interleaved)
 
+    def _slabs(self, n):
+        P = max(1, min(self.threads, n))
+        return [(a, b) for a, b in slab_bounds(n, P)]
+
+    def _parallel(self, fn, n):
+        """fn(a, b) on every slab [a, b) of n slices, results concatenated."""
+        slabs = self._slabs(n)
+        if len(slabs) == 1:
+            return fn(0, n)
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(len(slabs)) as pool:
+            parts = list(pool.map(lambda ab: fn(*ab), slabs))
+        return np.concatenate(parts, axis=0)
+
     def S(self, X):
-        """SumMPI over the five Kronecker terms (mpi_kron.py:77-90)."""
-        out = np.zeros_like(X)
-        for T, op in self.terms:
-            out += kron_apply(T, op, X)
-        return out
+        """SumMPI over the five Kronecker terms (mpi_kron.py:77-90): the time
+        stencils on the whole vector, the space chains slab by slab."""
+        TX = [apply_time(T, X) for T, _ in self.terms]
+
+        def slab(a, b):
+            out = np.zeros_like(X[a:b])
+            for (T, op), tx in zip(self.terms, TX):
+                out += apply_space(op, np.ascontiguousarray(tx[a:b]))
+            return out
+
+        return self._parallel(slab, X.shape[0])
 
     def WT_S_W(self, X):
         return self.WT(self.S(self.W(X)))  # mpi_kron.py:101-110
@@ -283,12 +307,16 @@ class HeatEqOracle:
     def P(self, X):
         """Block diagonal in time: slice t gets C_j A_x C_j with j = level of
         wavelet t (mpi_kron.py:122-132, heateq_mpi.py:159-162,183-184)."""
-        out = np.empty_like(X)
-        for j in np.unique(self.levels):
-            sel = np.nonzero(self.levels == j)[0]
-            C = self.C[j]
-            out[sel] = C(apply_space(self.prob.A_x, C(X[sel])))
-        return out
+        def slab(a, b):
+            out = np.empty_like(X[a:b])
+            lv = self.levels[a:b]
+            for j in np.unique(lv):
+                sel = np.nonzero(lv == j)[0]
+                C = self.C[j]
+                out[sel] = C(apply_space(self.prob.A_x, C(X[a:b][sel])))
+            return out
+
+        return self._parallel(slab, X.shape[0])
 
     def solve(self, **kw):
         return pcg(self.WT_S_W, self.P, self.rhs, **kw)

@@ -43,8 +43,10 @@ struct Level {
 // FIRST: first forward sweep from a zero initial guess = forward substitution
 // with the lower triangle, u_i = (f_i - sum_{j<i} a_ij u_j) / a_ii: entries
 // j >= i multiply zeros and are skipped, u is write-only (no memset needed).
+// 8 CTAs per SM (32 registers, a few spilled bytes): the kernel is bound by
+// memory latency x occupancy, full occupancy measured +10 % over 6 CTAs.
 template <int K, bool FIRST>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 8)
     k_gs_phase(const int *__restrict__ rows, int nrows, const int *__restrict__ indptr,
                const int *__restrict__ indices, const double *__restrict__ v0,
                const double *__restrict__ v1, const double *__restrict__ d0,

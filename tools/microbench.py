@@ -52,6 +52,10 @@ def main():
         print('%-34s %9.3f ms  %8.1f GB/s (alg, %4.0f B/dof)  %.3f of peak' %
               (name, ms, gbs, bytes_per_dof, gbs / peak), flush=True)
 
+    if args.only == 'wav':
+        timeit('wavelet W', lambda: heq.W._matvec(x, y), 16, reps=2)
+        timeit('wavelet WT', lambda: heq.WT._matvec(x, y), 16, reps=2)
+        return
     if args.only == 'mg':
         timeit('MG K_x apply (2 V(3,3))', lambda: heq.Kinv_x.apply_block(x.data, y.data), 523,
                reps=1)

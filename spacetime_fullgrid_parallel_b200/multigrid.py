@@ -135,6 +135,8 @@ class MultiGridFamily:
             lib().stk_mg_create(J + 1, smoothsteps, vcycles, K))
         assert self.handle.value, 'stk_mg_create failed'
         self.num_phases = []
+        self._levels = []  # per level: host values/diagonals + shared device arrays
+        self._uniform = {}  # coefs -> single-matrix handle
 
         def up(a, dt):
             t = torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(dev)
@@ -167,6 +169,11 @@ class MultiGridFamily:
                 ptr(d_vals[0]), ptr(d_vals[1]) if K == 2 else None,
                 ptr(d_diag[0]), ptr(d_diag[1]) if K == 2 else None,
                 ptr(d_order), phase_ptr.ctypes.data, len(phase_ptr) - 1))
+            self._levels.append({
+                'n': n, 'vals': vals, 'diags': diags, 'indptr': d_indptr,
+                'indices': d_indices, 'order': d_order, 'phase_ptr': phase_ptr,
+                'transfer': None
+            })
             if l >= 1:
                 P = sp.csr_matrix(hierarchy.P_mats[l - 1], dtype=np.float64)
                 R = sp.csr_matrix(hierarchy.R_mats[l - 1], dtype=np.float64)
@@ -177,14 +184,60 @@ class MultiGridFamily:
                       up(R.indices, np.int32), up(R.data, np.float64)]
                 check(lib().stk_mg_set_transfer(self.handle, l,
                                                 *[ptr(t) for t in tp]))
+                self._levels[-1]['transfer'] = tp
 
     def __del__(self):
         try:
+            for h, _ in list(getattr(self, '_uniform', {}).values()):
+                lib().stk_mg_destroy(h)
+            self._uniform = {}
             if self.handle and self.handle.value:
                 lib().stk_mg_destroy(self.handle)
                 self.handle = None
         except Exception:
             pass
+
+    def uniform_handle(self, coefs):
+        """Single-matrix (K = 1) hierarchy of sum_k coefs[k] * base_mats[k] for
+        blocks whose slices all share the coefficients (K_x in S): the level
+        values are combined once on the host -- which is what the reference
+        does (heateq_mpi.py:97-98) -- so the kernels read one value array and
+        no per-slice coefficients.  Pattern, schedule and transfer operators
+        are shared with the family."""
+        coefs = tuple(float(c) for c in coefs)
+        if coefs not in self._uniform:
+            h = ctypes.c_void_p(lib().stk_mg_create(
+                len(self._levels), self.smoothsteps, self.vcycles, 1))
+            assert h.value, 'stk_mg_create failed'
+            keep = []
+            for l, lv in enumerate(self._levels):
+                vals = sum(c * v for c, v in zip(coefs, lv['vals']))
+                diag = sum(c * d for c, d in zip(coefs, lv['diags']))
+                dv = torch.from_numpy(np.ascontiguousarray(vals)).to(self.device)
+                dd = torch.from_numpy(np.ascontiguousarray(diag)).to(self.device)
+                keep += [dv, dd]
+                check(lib().stk_mg_set_level(
+                    h, l, lv['n'], ptr(lv['indptr']), ptr(lv['indices']),
+                    ptr(dv), None, ptr(dd), None, ptr(lv['order']),
+                    lv['phase_ptr'].ctypes.data, len(lv['phase_ptr']) - 1))
+                if lv['transfer'] is not None:
+                    check(lib().stk_mg_set_transfer(
+                        h, l, *[ptr(t) for t in lv['transfer']]))
+            inv = torch.from_numpy(np.ascontiguousarray(
+                self.coarse_inverse(coefs))).to(self.device)
+            keep.append(inv)
+            self._uniform[coefs] = (h, keep)
+        return self._uniform[coefs]
+
+    def apply_uniform(self, coefs, b, x):
+        """x <- MG(sum_k coefs[k] B_k) b, the same matrix for every slice."""
+        if self.K == 1:
+            return self.apply_block(b, x, self.context([coefs], b.shape[1]))
+        h, keep = self.uniform_handle(coefs)
+        ld = b.shape[1]
+        ws = _workspace(b.device, lib().stk_mg_workspace(h, ld))
+        check(lib().stk_mg_apply(h, None, None, ptr(keep[-1]), None, ptr(b),
+                                 ptr(x), ld, ptr(ws), stream()))
 
     def coarse_inverse(self, coefs):
         """Dense inverse of the coarsest matrix (the reference factorises it
@@ -248,9 +301,9 @@ class MultiGrid:
 
     def apply_block(self, x, out, ctx=None):
         if ctx is None:
-            ld = x.shape[1]
-            ctx = self.family.context([self.coefs], ld)
-        self.family.apply_block(x, out, ctx)
+            self.family.apply_uniform(self.coefs, x, out)
+        else:
+            self.family.apply_block(x, out, ctx)
         self.num_applies += 1
 
     # SciPy LinearOperator-style host interface (M,) / (M, k)

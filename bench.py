@@ -321,6 +321,14 @@ def run_stk(args):
     }
     del u
 
+    if args.no_e2e:  # profiling runs: skip the full solve and the CPU leg
+        if rank == 0:
+            print(json.dumps({'ms_per_step': ms_per_step, 'value': value,
+                              'gpu_launches': int(launches),
+                              'roofline': roofline, 'note': 'profiling run'}),
+                  flush=True)
+        return
+
     # ---- e2e: the user's call, host buffers in and out ----
     a, b = heq.rhs.t_begin, heq.rhs.t_end
     rhs_host = torch.from_numpy(
@@ -378,6 +386,8 @@ def main():
     ap.add_argument('--impl', default='stk', choices=['stk', 'reference'])
     ap.add_argument('--J_time', type=int, default=8)
     ap.add_argument('--J_space', type=int, default=9)
+    ap.add_argument('--no-e2e', dest='no_e2e', action='store_true',
+                    help='profiling runs: timed iterations and roofline only')
     ap.add_argument('--no-cpu', dest='no_cpu', action='store_true',
                     help='skip the cpu_baseline leg (profiling runs)')
     args = ap.parse_args()

@@ -84,6 +84,11 @@ __global__ void __launch_bounds__(256)
         int t = (int)(k - i * ld2) * 2;
         size_t o = (size_t)i * ldy + t;
         const double *xi = x + (size_t)i * ldx;
+        if (ACC) {  // rows of T without entries leave y untouched (G_t = e0 e0^T)
+            bool e0 = t >= nrows_t || __ldg(indptr + t) == __ldg(indptr + t + 1);
+            bool e1 = t + 1 >= nrows_t || __ldg(indptr + t + 1) == __ldg(indptr + t + 2);
+            if (e0 && e1 && beta == 1.0) continue;
+        }
         double2 out = make_double2(0.0, 0.0);
         if (t < nrows_t)
             out.x = alpha * time_row(t, indptr, indices, vals, xi, ncols_local, xh, M, i);
@@ -93,6 +98,118 @@ __global__ void __launch_bounds__(256)
             double2 old = ldv2(y + o);
             out.x = fma(beta, old.x, out.x);
             out.y = fma(beta, old.y, out.y);
+        }
+        stv2(y + o, out);
+    }
+}
+
+// Two-input form: y = alpha * [Ta Tb] [x0; x1] + beta * y.  Column c of the
+// stacked matrix addresses x0 (c < n), x1 (c < 2n), the halo of x0, then the
+// halo of x1.  Serves the brackets (A_t (x) M + L_t (x) A) x of the regrouped
+// Schur operator in one pass over M x and A x.
+__device__ __forceinline__ double time_row2(int t, const int *__restrict__ indptr,
+                                            const int *__restrict__ indices,
+                                            const double *__restrict__ vals,
+                                            const double *__restrict__ x0i,
+                                            const double *__restrict__ x1i, int n, int nh0,
+                                            const double *__restrict__ xh0,
+                                            const double *__restrict__ xh1, int M, unsigned i) {
+    double s = 0.0;
+    int p1 = __ldg(indptr + t + 1);
+    for (int p = __ldg(indptr + t); p < p1; ++p) {
+        int c = __ldg(indices + p);
+        double xv;
+        if (c < n) xv = x0i[c];
+        else if (c < 2 * n) xv = x1i[c - n];
+        else if (c < 2 * n + nh0) xv = __ldg(xh0 + (size_t)(c - 2 * n) * M + i);
+        else xv = __ldg(xh1 + (size_t)(c - 2 * n - nh0) * M + i);
+        s = fma(__ldg(vals + p), xv, s);
+    }
+    return s;
+}
+
+template <bool ACC>
+__global__ void __launch_bounds__(256)
+    k_time_apply2(int M, int nrows_t, const int *__restrict__ indptr,
+                  const int *__restrict__ indices, const double *__restrict__ vals,
+                  const double *__restrict__ x0, const double *__restrict__ x1, int ldx, int n,
+                  const double *__restrict__ xh0, int nh0, const double *__restrict__ xh1,
+                  double alpha, double beta, double *__restrict__ y, int ldy) {
+    const unsigned ld2 = (unsigned)ldy / 2u;
+    const unsigned total = (unsigned)M * ld2;
+    const unsigned stride = gridDim.x * 256u;
+    for (unsigned k = blockIdx.x * 256u + threadIdx.x; k < total; k += stride) {
+        unsigned i = k / ld2;
+        int t = (int)(k - i * ld2) * 2;
+        size_t o = (size_t)i * ldy + t;
+        const double *x0i = x0 + (size_t)i * ldx, *x1i = x1 + (size_t)i * ldx;
+        double2 out = make_double2(0.0, 0.0);
+        if (t < nrows_t)
+            out.x = alpha * time_row2(t, indptr, indices, vals, x0i, x1i, n, nh0, xh0, xh1, M, i);
+        if (t + 1 < nrows_t)
+            out.y = alpha *
+                    time_row2(t + 1, indptr, indices, vals, x0i, x1i, n, nh0, xh0, xh1, M, i);
+        if (ACC) {
+            double2 old = ldv2(y + o);
+            out.x = fma(beta, old.x, out.x);
+            out.y = fma(beta, old.y, out.y);
+        }
+        stv2(y + o, out);
+    }
+}
+
+// y0 = A0 x and y1 = A1 x for two matrices on one sparsity pattern: x and the
+// pattern are read once (M_x x and A_x x of heateq_mpi.py:166-178).
+__global__ void __launch_bounds__(256)
+    k_space_spmm_split(int nrows, const int *__restrict__ indptr, const int *__restrict__ indices,
+                       const double *__restrict__ vals0, const double *__restrict__ vals1,
+                       const double *__restrict__ x, double *__restrict__ y0,
+                       double *__restrict__ y1, int ld, unsigned ld2) {
+    const unsigned total = (unsigned)nrows * ld2;
+    const unsigned stride = gridDim.x * 256u;
+    for (unsigned k = blockIdx.x * 256u + threadIdx.x; k < total; k += stride) {
+        unsigned i = k / ld2;
+        unsigned c = (k - i * ld2) * 2u;
+        int p0 = __ldg(indptr + i), p1 = __ldg(indptr + i + 1);
+        double2 s0 = make_double2(0.0, 0.0), s1 = make_double2(0.0, 0.0);
+        row_product<2, 0>(p0, p1, indices, vals0, vals1, x, ld, c, s0, s1);
+        size_t o = (size_t)i * ld + c;
+        stv2(y0 + o, s0);
+        stv2(y1 + o, s1);
+    }
+}
+
+// y = alpha * (A0 x0 + A1 x1) + beta * z on one sparsity pattern
+// ((I (x) M) z1 + (I (x) A) z2 of the regrouped Schur operator).
+template <bool HAS_Z>
+__global__ void __launch_bounds__(256)
+    k_space_spmm_pair(int nrows, const int *__restrict__ indptr, const int *__restrict__ indices,
+                      const double *__restrict__ vals0, const double *__restrict__ vals1,
+                      const double *__restrict__ x0, const double *__restrict__ x1, double alpha,
+                      double beta, const double *z, double *y, int ld, unsigned ld2) {
+    const unsigned total = (unsigned)nrows * ld2;
+    const unsigned stride = gridDim.x * 256u;
+    for (unsigned k = blockIdx.x * 256u + threadIdx.x; k < total; k += stride) {
+        unsigned i = k / ld2;
+        unsigned c = (k - i * ld2) * 2u;
+        int p1 = __ldg(indptr + i + 1);
+        double2 s = make_double2(0.0, 0.0);
+        for (int p = __ldg(indptr + i); p < p1; ++p) {
+            size_t off = (size_t)__ldg(indices + p) * ld + c;
+            double2 a = ldv2(x0 + off), b = ldv2(x1 + off);
+            double m = __ldg(vals0 + p), w = __ldg(vals1 + p);
+            s.x = fma(m, a.x, fma(w, b.x, s.x));
+            s.y = fma(m, a.y, fma(w, b.y, s.y));
+        }
+        size_t o = (size_t)i * ld + c;
+        double2 out;
+        if (HAS_Z) {
+            double2 zv = ldv2(z + o);
+            out.x = fma(alpha, s.x, beta * zv.x);
+            out.y = fma(alpha, s.y, beta * zv.y);
+        } else {
+            out.x = alpha * s.x;
+            out.y = alpha * s.y;
         }
         stv2(y + o, out);
     }
@@ -282,6 +399,63 @@ int stk_time_apply(int M, int nrows_t, int nnz, const int *indptr, const int *in
         k_time_apply<false><<<resident_grid(k_time_apply<false>, 256, work), 256, 0, s>>>(
             M, nrows_t, indptr, indices, vals, x, ldx, ncols_local, xh, alpha, beta, y, ldy);
     return check_launch("k_time_apply");
+}
+
+int stk_time_apply2(int M, int nrows_t, const int *indptr, const int *indices,
+                    const double *vals, const double *x0, const double *x1, int ldx,
+                    int ncols_local, const double *xh0, int n_halo0, const double *xh1,
+                    double alpha, double beta, double *y, int ldy, void *stream) {
+    if (x0 == y || x1 == y) return fail(-1, "stk_time_apply2: inputs must not alias y");
+    if (nrows_t > ldy || (ldy & 1)) return fail(-1, "stk_time_apply2: bad pitch of y");
+    if (M == 0) return 0;
+    int64_t work = (int64_t)M * (ldy / 2);
+    if (work >= (1ll << 32)) return fail(-2, "stk_time_apply2: block too large");
+    cudaStream_t s = as_stream(stream);
+    if (beta != 0.0)
+        k_time_apply2<true><<<resident_grid(k_time_apply2<true>, 256, work), 256, 0, s>>>(
+            M, nrows_t, indptr, indices, vals, x0, x1, ldx, ncols_local, xh0, n_halo0, xh1, alpha,
+            beta, y, ldy);
+    else
+        k_time_apply2<false><<<resident_grid(k_time_apply2<false>, 256, work), 256, 0, s>>>(
+            M, nrows_t, indptr, indices, vals, x0, x1, ldx, ncols_local, xh0, n_halo0, xh1, alpha,
+            beta, y, ldy);
+    return check_launch("k_time_apply2");
+}
+
+int stk_space_spmm_split(int nrows, const int *indptr, const int *indices, const double *vals0,
+                         const double *vals1, const double *x, double *y0, double *y1, int ld,
+                         void *stream) {
+    if (ld & 3) return fail(-1, "stk_space_spmm_split: pitch must be a multiple of 4");
+    if (x == y0 || x == y1 || y0 == y1) return fail(-1, "stk_space_spmm_split: aliasing");
+    if (nrows == 0) return 0;
+    unsigned ld2 = (unsigned)ld / 2u;
+    int64_t work = (int64_t)nrows * ld2;
+    if (work >= (1ll << 32)) return fail(-2, "stk_space_spmm_split: block too large");
+    k_space_spmm_split<<<resident_grid(k_space_spmm_split, 256, work), 256, 0,
+                         as_stream(stream)>>>(nrows, indptr, indices, vals0, vals1, x, y0, y1, ld,
+                                              ld2);
+    return check_launch("k_space_spmm_split");
+}
+
+int stk_space_spmm_pair(int nrows, const int *indptr, const int *indices, const double *vals0,
+                        const double *vals1, const double *x0, const double *x1, double alpha,
+                        double beta, const double *z, double *y, int ld, void *stream) {
+    if (ld & 3) return fail(-1, "stk_space_spmm_pair: pitch must be a multiple of 4");
+    if (x0 == y || x1 == y) return fail(-1, "stk_space_spmm_pair: inputs must not alias y");
+    if (beta != 0.0 && !z) return fail(-1, "stk_space_spmm_pair: beta != 0 needs z");
+    if (nrows == 0) return 0;
+    unsigned ld2 = (unsigned)ld / 2u;
+    int64_t work = (int64_t)nrows * ld2;
+    if (work >= (1ll << 32)) return fail(-2, "stk_space_spmm_pair: block too large");
+    cudaStream_t s = as_stream(stream);
+    if (beta != 0.0)
+        k_space_spmm_pair<true><<<resident_grid(k_space_spmm_pair<true>, 256, work), 256, 0, s>>>(
+            nrows, indptr, indices, vals0, vals1, x0, x1, alpha, beta, z, y, ld, ld2);
+    else
+        k_space_spmm_pair<false><<<resident_grid(k_space_spmm_pair<false>, 256, work), 256, 0,
+                                   s>>>(nrows, indptr, indices, vals0, vals1, x0, x1, alpha, beta,
+                                        z, y, ld, ld2);
+    return check_launch("k_space_spmm_pair");
 }
 
 int stk_pack_slices(const double *x, int ld, int M, const int *tidx, int n, double *out,

@@ -32,10 +32,10 @@ from .linop import CompositeLinOp
 import scipy.sparse as sp
 import torch
 
-from .linop import as_space_op
+from .linop import DeviceCSRPair, as_space_op
 from .mpi_kron import (BlockDiagMPI, CompositeMPI, LinearOperatorMPI,
                        MatKronIdentityMPI, SumMPI, TridiagKronMatMPI)
-from .timeop import TimeOpPlan
+from .timeop import TimeOpPlan, TimeOpPlan2
 from .mpi_shared_mem import shared_sparse_matrix
 from .mpi_vector import DofDistributionMPI, KronVectorMPI
 from .multigrid import MultiGrid, MultiGridFamily
@@ -61,36 +61,33 @@ class SchurOperatorMPI(LinearOperatorMPI):
     and share one +-1-slice halo exchange each."""
     def __init__(self, dofs_distr, A_t, L_t, M_t, G_t, M_x, A_x, Kinv_x):
         super().__init__(dofs_distr)
-        self.M_x, self.A_x, self.K = (as_space_op(M_x), as_space_op(A_x),
-                                      as_space_op(Kinv_x))
-        self.plans = {
+        self.K = as_space_op(Kinv_x)
+        self.MA = DeviceCSRPair(M_x, A_x)  # both on one sparsity pattern
+        plans = {
             name: TimeOpPlan(dofs_distr, sp.csr_matrix(T))
             for name, T in (('A', A_t), ('L', L_t), ('LT', L_t.T.tocsr()),
                             ('M', M_t), ('G', G_t))
         }
+        self.plans = plans
+        self.bracket1 = TimeOpPlan2(plans['A'], plans['L'])
+        self.bracket2 = TimeOpPlan2(plans['LT'], plans['M'])
 
     def _matvec(self, vec_in, vec_out):
         assert vec_in is not vec_out
         c0 = sum(getattr(p, 'time_communication', 0.0)
                  for p in self.plans.values())
         mx, ax = vec_in.empty_like(), vec_in.empty_like()
-        self.M_x.apply_block(vec_in.data, mx.data)
-        self.A_x.apply_block(vec_in.data, ax.data)
+        self.MA.split(vec_in.data, mx.data, ax.data)  # M x and A x, one pass
         y = torch.empty_like(vec_in.data)
-        z = torch.empty_like(vec_in.data)
+        z1 = torch.empty_like(vec_in.data)
+        z2 = torch.empty_like(vec_in.data)
         vec_out._invalidate()
-        # first bracket -> K -> M
-        self.plans['A'].apply(mx, y)
-        self.plans['L'].apply(ax, y, 1.0, 1.0)
-        self.K.apply_block(y, z)
-        self.M_x.spmm(z, vec_out.data)
-        # second bracket -> K -> A, accumulated
-        self.plans['LT'].apply(mx, y)
-        self.plans['M'].apply(ax, y, 1.0, 1.0)
-        self.K.apply_block(y, z)
-        self.A_x.spmm(z, vec_out.data, 1.0, 1.0, vec_out.data)
-        # G_t (x) M
-        self.plans['G'].apply(mx, vec_out.data, 1.0, 1.0)
+        self.bracket1.apply(mx, ax, y)  # A_t M x + L_t A x
+        self.K.apply_block(y, z1)
+        self.bracket2.apply(mx, ax, y)  # L_t^T M x + M_t A x
+        self.K.apply_block(y, z2)
+        self.MA.pair(z1, z2, vec_out.data)  # M z1 + A z2
+        self.plans['G'].apply(mx, vec_out.data, 1.0, 1.0)  # + G_t (x) M x
         self.time_communication += sum(
             getattr(p, 'time_communication', 0.0)
             for p in self.plans.values()) - c0

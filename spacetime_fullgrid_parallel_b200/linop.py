@@ -61,6 +61,55 @@ class DeviceCSR:
         return host_apply(self, B)
 
 
+class DeviceCSRPair:
+    """Two matrices on their union sparsity pattern (M_x and A_x): one index
+    structure, two value arrays, so that products with both read the pattern
+    and the input block once (stk_space_spmm_split / _pair)."""
+    def __init__(self, mat0, mat1, device=None):
+        if device is None:
+            from .mpi_vector import _device
+            device = _device()
+        m0 = sp.csr_matrix(mat0.host if isinstance(mat0, DeviceCSR) else mat0,
+                           dtype=np.float64)
+        m1 = sp.csr_matrix(mat1.host if isinstance(mat1, DeviceCSR) else mat1,
+                           dtype=np.float64)
+        assert m0.shape == m1.shape
+        pat = (abs(m0) + abs(m1)).tocsr()
+        pat.sort_indices()
+        n = pat.shape[1]
+        rows = np.repeat(np.arange(pat.shape[0], dtype=np.int64),
+                         np.diff(pat.indptr))
+        keys = rows * n + pat.indices
+
+        def project(m):
+            m.sort_indices()
+            r = np.repeat(np.arange(m.shape[0], dtype=np.int64),
+                          np.diff(m.indptr))
+            vals = np.zeros(len(keys))
+            vals[np.searchsorted(keys, r * n + m.indices)] = m.data
+            return torch.from_numpy(vals).to(device)
+
+        self.shape = pat.shape
+        self.indptr = torch.from_numpy(pat.indptr.astype(np.int32)).to(device)
+        self.indices = torch.from_numpy(pat.indices.astype(np.int32)).to(device)
+        self.vals0, self.vals1 = project(m0), project(m1)
+
+    def split(self, x, y0, y1):
+        """y0 = mat0 x, y1 = mat1 x."""
+        check(lib().stk_space_spmm_split(self.shape[0], ptr(self.indptr),
+                                         ptr(self.indices), ptr(self.vals0),
+                                         ptr(self.vals1), ptr(x), ptr(y0),
+                                         ptr(y1), x.shape[1], stream()))
+
+    def pair(self, x0, x1, out, alpha=1.0, beta=0.0, z=None):
+        """out = alpha (mat0 x0 + mat1 x1) + beta z."""
+        check(lib().stk_space_spmm_pair(self.shape[0], ptr(self.indptr),
+                                        ptr(self.indices), ptr(self.vals0),
+                                        ptr(self.vals1), ptr(x0), ptr(x1),
+                                        float(alpha), float(beta), ptr(z),
+                                        ptr(out), x0.shape[1], stream()))
+
+
 _csr_cache = {}
 
 

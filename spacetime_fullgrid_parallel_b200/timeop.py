@@ -183,6 +183,47 @@ class TimeOpPlan:
                                           1.0, 1.0, stream()))
 
 
+class TimeOpPlan2:
+    """out = (Ta (x) I) va + (Tb (x) I) vb in one pass: the two local CSRs
+    stacked side by side, columns [va | vb | halo of va | halo of vb]."""
+    def __init__(self, plan_a, plan_b):
+        assert plan_a.n_loc == plan_b.n_loc
+        self.a, self.b = plan_a, plan_b
+        n, ha, hb = plan_a.n_loc, plan_a.n_halo, plan_b.n_halo
+
+        def shifted(loc, col_shift, halo_shift):
+            loc = loc.tocoo()
+            cols = np.where(loc.col < n, loc.col + col_shift,
+                            loc.col - n + halo_shift)
+            return sp.coo_matrix((loc.data, (loc.row, cols)),
+                                 shape=(n, 2 * n + ha + hb))
+
+        self.local = (shifted(plan_a.local, 0, 2 * n)
+                      + shifted(plan_b.local, n, 2 * n + ha)).tocsr()
+        self.local.sort_indices()
+        self._dev = None
+
+    def apply(self, va, vb, out_block, alpha=1.0, beta=0.0):
+        import torch
+        from ._lib import check, lib, ptr, stream
+        dev = va.data.device
+        if self._dev is None:
+            self._dev = tuple(
+                torch.from_numpy(a).to(dev)
+                for a in (self.local.indptr.astype(np.int32),
+                          self.local.indices.astype(np.int32),
+                          self.local.data.astype(np.float64)))
+        indptr, indices, vals = self._dev
+        ha = self.a.fetch(va) if self.a.n_halo else None
+        hb = self.b.fetch(vb) if self.b.n_halo else None
+        check(lib().stk_time_apply2(va.M, self.a.n_loc, ptr(indptr),
+                                    ptr(indices), ptr(vals), ptr(va.data),
+                                    ptr(vb.data), va.ld, self.a.n_loc,
+                                    ptr(ha), self.a.n_halo, ptr(hb),
+                                    float(alpha), float(beta), ptr(out_block),
+                                    va.ld, stream()))
+
+
 def _now():
     import time
     return time.perf_counter()

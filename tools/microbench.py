@@ -104,6 +104,14 @@ def main():
     timeit('time tridiag A_t', lambda: heq.A_MKM.T_I._matvec(x, y), 16)
     timeit('wavelet W', lambda: heq.W._matvec(x, y), 16)
     timeit('wavelet WT', lambda: heq.WT._matvec(x, y), 16)
+    if hasattr(heq.S, 'MA'):
+        S = heq.S
+        mx, ax = x.empty_like(), x.empty_like()
+        z1 = torch.empty_like(x.data)
+        timeit('S: split (Mx, Ax)', lambda: S.MA.split(x.data, mx.data, ax.data), 24)
+        timeit('S: bracket (2-input time op)', lambda: S.bracket1.apply(mx, ax, y.data), 24)
+        timeit('S: pair (M z1 + A z2)', lambda: S.MA.pair(mx.data, ax.data, z1), 24)
+        timeit('S: G term', lambda: S.plans['G'].apply(mx, z1, 1.0, 1.0), 24)
     timeit('S apply', lambda: heq.S._matvec(x, y), 1300)
     timeit('P apply', lambda: heq.P._matvec(x, y), 1100)
     timeit('dot', lambda: x.dot_device(y), 16)

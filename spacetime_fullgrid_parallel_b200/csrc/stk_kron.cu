@@ -364,7 +364,13 @@ int stk_time_apply(int M, int nrows_t, int nnz, const int *indptr, const int *in
     // shared-memory kernel when the matrix and a panel of >= 8 columns fit.
     const int W = (ncols_local + n_halo) | 1;  // odd pitch: conflict-free column walks
     const size_t mat_bytes = (size_t)nnz * 12 + (size_t)(nrows_t + 1) * 4 + 16;
-    const size_t budget = 72 * 1024;
+    // 72 KB leaves room for 3 CTAs per SM; larger matrices take one CTA's 200 KB.
+    size_t budget = 72 * 1024;
+    int ctas_per_sm = 3;
+    if (mat_bytes + (size_t)8 * W * 8 > budget) {
+        budget = 200 * 1024;
+        ctas_per_sm = 1;
+    }
     if (nnz > 4 * (int64_t)nrows_t && mat_bytes + (size_t)8 * W * 8 <= budget) {
         int RB = (int)((budget - mat_bytes) / ((size_t)W * 8));
         if (RB > 64) RB = 64;
@@ -376,7 +382,7 @@ int stk_time_apply(int M, int nrows_t, int nnz, const int *indptr, const int *in
                                                cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                (int)budget),
                           "stk_time_apply: smem attribute"));
-            int64_t cap = (int64_t)sm_count() * 3;
+            int64_t cap = (int64_t)sm_count() * ctas_per_sm;
             k_time_apply_smem<true><<<(unsigned)(ntiles < cap ? ntiles : cap), 256, smem, s>>>(
                 M, nrows_t, nnz, indptr, indices, vals, x, ldx, ncols_local, xh, n_halo, alpha,
                 beta, y, ldy, RB, W);
@@ -385,7 +391,7 @@ int stk_time_apply(int M, int nrows_t, int nnz, const int *indptr, const int *in
                                                cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                (int)budget),
                           "stk_time_apply: smem attribute"));
-            int64_t cap = (int64_t)sm_count() * 3;
+            int64_t cap = (int64_t)sm_count() * ctas_per_sm;
             k_time_apply_smem<false><<<(unsigned)(ntiles < cap ? ntiles : cap), 256, smem, s>>>(
                 M, nrows_t, nnz, indptr, indices, vals, x, ldx, ncols_local, xh, n_halo, alpha,
                 beta, y, ldy, RB, W);

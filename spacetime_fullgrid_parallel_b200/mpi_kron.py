@@ -23,7 +23,14 @@ def as_matrix(operator):
 
 
 class LinearOperatorMPI:
-    """Base class (mpi_kron.py:13-59)."""
+    """Base class (mpi_kron.py:13-59).
+
+    Kernels are enqueued asynchronously, so by default `time_applies` counts
+    host time only.  Set `LinearOperatorMPI.sync_timing = True` (the timing
+    driver does) to bracket every `@` with a device synchronisation and get the
+    reference's meaning: wall time until the result exists."""
+    sync_timing = False
+
     def __init__(self, dofs_distr):
         self.dofs_distr = dofs_distr
         self.N = dofs_distr.N
@@ -34,8 +41,12 @@ class LinearOperatorMPI:
 
     def __matmul__(self, x):
         assert isinstance(x, KronVectorMPI)
+        if LinearOperatorMPI.sync_timing:
+            torch.cuda.synchronize()
         start = Wtime()
         y = self._matvec(x, x.empty_like())
+        if LinearOperatorMPI.sync_timing:
+            torch.cuda.synchronize()
         self.num_applies += 1
         self.time_applies += Wtime() - start
         return y
@@ -227,30 +238,65 @@ class MatKronIdentityMPI(LinearOperatorMPI):
         self.T = T
         self.pplan = plan_for(dofs_distr)
         self._dev = None
+        self._pos = None
 
-    def _matvec(self, vec_in, vec_out):
+    def _apply_time(self, sblock):
+        """mat_time along the (complete, contiguous) time axis of a
+        space-sharded block.  A wavelet transform runs as in-place lifting
+        (level-wise ordering: plus the column permutation to/from node order);
+        any other matrix goes through the sparse time-operator kernel."""
+        from .wavelets import WaveletTransformOp, levelwise_positions
+        op = self.mat_time
+        if isinstance(op, WaveletTransformOp):
+            N = self.N
+            if op.interleaved:
+                res = sblock.clone()
+            else:
+                if self._pos is None:
+                    self._pos = torch.from_numpy(
+                        levelwise_positions(op.J)).to(sblock.device)
+                res = torch.zeros_like(sblock)
+                if not op.transposed:  # coefficients to their nodes
+                    res[:, self._pos] = sblock[:, :N]
+                else:
+                    res[:, :N] = sblock[:, :N]
+            check(lib().stk_wavelet_lift(res.shape[0], op.J,
+                                         int(op.transposed), ptr(res),
+                                         res.shape[1], stream()))
+            if not op.interleaved and op.transposed:
+                out = torch.zeros_like(res)
+                out[:, :N] = res[:, self._pos]
+                res = out
+            return res
         if self._dev is None:
-            dev = vec_in.data.device
+            dev = sblock.device
             self._dev = tuple(
                 torch.from_numpy(a).to(dev)
                 for a in (self.T.indptr.astype(np.int32),
                           self.T.indices.astype(np.int32),
                           self.T.data.astype(np.float64)))
         indptr, indices, vals = self._dev
-        start = Wtime()
-        sblock = self.pplan.forward(vec_in.data, vec_in.n_loc, vec_in.ld)
-        self.time_communication += Wtime() - start
         res = torch.empty_like(sblock)
         check(lib().stk_time_apply(sblock.shape[0], self.N, self.T.nnz,
                                    ptr(indptr), ptr(indices), ptr(vals),
                                    ptr(sblock), sblock.shape[1], self.N, None,
                                    0, 1.0, 0.0, ptr(res), res.shape[1],
                                    stream()))
-        start = Wtime()
-        out = self.pplan.backward(res, vec_in.n_loc, vec_in.ld)
-        self.time_communication += Wtime() - start
+        return res
+
+    def _matvec(self, vec_in, vec_out):
         vec_out._invalidate()
-        vec_out.data = out
+        if self.dofs_distr.size == 1:
+            # one rank: the block already holds the whole time axis per dof
+            vec_out.data = self._apply_time(vec_in.data)
+            return vec_out
+        start = Wtime()
+        sblock = self.pplan.forward(vec_in.data, vec_in.n_loc, vec_in.ld)
+        self.time_communication += Wtime() - start
+        res = self._apply_time(sblock)
+        start = Wtime()
+        vec_out.data = self.pplan.backward(res, vec_in.n_loc, vec_in.ld)
+        self.time_communication += Wtime() - start
         return vec_out
 
 

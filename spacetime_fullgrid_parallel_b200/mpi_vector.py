@@ -285,6 +285,36 @@ class KronVectorMPI:
         from .permute import permute_vector
         return permute_vector(self)
 
+    def communicate_dofs(self, dofs):
+        """Fetch the time slices with the given GLOBAL indices that live on
+        other ranks (mpi_vector.py:189-203; every rank must call it with the
+        needs of its own rows of a symmetric-pattern time matrix, passed as
+        (row, col) pairs or as a plain list of columns).  Returns
+        {global index: device row of M doubles}."""
+        import scipy.sparse as sp
+        from .timeop import TimeOpPlan
+        cols = sorted({int(d[1]) if np.ndim(d) else int(d) for d in dofs})
+        cols = [c for c in cols if not self.t_begin <= c < self.t_end]
+        # the exchange pattern must be known to both sides: gather the needs
+        all_needs = self._gather_needs(cols)
+        rows, cs = [], []
+        for p, need in enumerate(all_needs):
+            a, _ = self.dofs_distr.dof_distribution[p]
+            rows += [a] * len(need)
+            cs += list(need)
+        T = sp.csr_matrix((np.ones(len(rows)), (rows, cs)),
+                          shape=(self.N, self.N))
+        plan = TimeOpPlan(self.dofs_distr, T)
+        halo = plan.fetch(self)
+        return {int(c): halo[k] for k, c in enumerate(plan.halo_cols)}
+
+    def _gather_needs(self, cols):
+        comm = self.dofs_distr.comm
+        if self.dofs_distr.size == 1:
+            return [cols]
+        gathered = comm.gather(cols)
+        return comm.bcast(gathered)
+
     # -- halo (mpi_vector.py:140-203) -------------------------------------
     def communicate_bdr(self, callback=None):
         """Fetch the last slice of the previous rank and the first slice of the

@@ -272,6 +272,62 @@ class MultiGridFamily:
                          _family=self, _coefs=coefs)
 
 
+class Smoother:
+    """Lexicographic Gauss-Seidel on one level matrix (the semantics of
+    multigrid.py:83-97 / PETScSMoother :100-127), on the device: host arrays
+    u, f of shape (n,) or (n, k); `PreSmooth` sweeps forward, `PostSmooth`
+    backward, `its` times, updating u in place."""
+    def __init__(self, mat, its=1):
+        self.its = its
+        mat = sp.csr_matrix(mat, dtype=np.float64)
+        mat.sort_indices()
+        self.n = mat.shape[0]
+        self.device = dev = _device()
+        order, phase_ptr = gauss_seidel_schedule(mat.indptr, mat.indices)
+        self._keep = [
+            torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(dev)
+            for a, dt in ((mat.indptr, np.int32), (mat.indices, np.int32),
+                          (mat.data, np.float64), (mat.diagonal(), np.float64),
+                          (order, np.int32))
+        ]
+        self.handle = ctypes.c_void_p(lib().stk_mg_create(2, its, 1, 1))
+        ip, ix, dv, dd, od = self._keep
+        check(lib().stk_mg_set_level(self.handle, 1, self.n, ptr(ip), ptr(ix),
+                                     ptr(dv), None, ptr(dd), None, ptr(od),
+                                     phase_ptr.ctypes.data,
+                                     len(phase_ptr) - 1))
+
+    def __del__(self):
+        try:
+            if self.handle and self.handle.value:
+                lib().stk_mg_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def _sweep(self, u, f, backward):
+        from .mpi_vector import pitch
+        u2 = np.asarray(u, dtype=np.float64).reshape(self.n, -1)
+        f2 = np.asarray(f, dtype=np.float64).reshape(self.n, -1)
+        k = u2.shape[1]
+        ld = pitch(k)
+        dev = self.device
+        du = torch.zeros((self.n, ld), dtype=torch.float64, device=dev)
+        df = torch.zeros((self.n, ld), dtype=torch.float64, device=dev)
+        du[:, :k] = torch.from_numpy(np.ascontiguousarray(u2)).to(dev)
+        df[:, :k] = torch.from_numpy(np.ascontiguousarray(f2)).to(dev)
+        check(lib().stk_mg_smooth(self.handle, 1, self.its,
+                                  int(backward), None, None, ptr(df), ptr(du),
+                                  ld, stream()))
+        u[...] = du[:, :k].cpu().numpy().reshape(np.shape(u))
+
+    def PreSmooth(self, u, f):
+        self._sweep(u, f, False)
+
+    def PostSmooth(self, u, f):
+        self._sweep(u, f, True)
+
+
 class MultiGrid:
     """V-cycle preconditioner for one matrix (multigrid.py:130-197)."""
     def __init__(self, mat, hierarchy, smoothsteps=2, vcycles=1, _family=None,

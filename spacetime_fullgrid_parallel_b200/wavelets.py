@@ -74,6 +74,12 @@ def _level_step(J, j):
     return step
 
 
+def WaveletTransformMat(J):
+    """The level-wise transform as an explicit sparse matrix (the debugging
+    aid of wavelets.py:9-42)."""
+    return WaveletTransformOp(J, interleaved=False).as_matrix()
+
+
 class WaveletTransformOp:
     """W: wavelet coordinates -> hat coordinates along axis 0 of an (N, k)
     array, N = 2^J + 1 (wavelets.py:45-169)."""

@@ -54,7 +54,7 @@ int sm_count();
 // than are resident at once (SMs x occupancy), so that no CTA is launched
 // behind another one: on B200 a CTA that lives only a few microseconds costs
 // ~20 % of the achievable HBM bandwidth in launch/drain overhead (measured,
-// profiles/r1b_gs_variants.md).
+// profiles/r1_experiments.md).
 template <class Kernel>
 inline unsigned resident_grid(Kernel kernel, int threads, int64_t work) {
     static thread_local std::unordered_map<const void *, int> cache;
@@ -85,67 +85,25 @@ __device__ __forceinline__ double2 ldg2(const double *p) {
 
 // Row product of a (K-valued) CSR row with the block, for one double2 column:
 //   s0 += sum_p v0[p] * x[indices[p], c..c+1]   (s1 likewise with v1, K == 2).
-// The first UNROLL nonzeros are loaded as one batch -- all indices and values,
-// then all x values -- so that up to UNROLL independent 16-byte loads are in
-// flight per thread instead of one dependent chain per nonzero (the rows of
-// P1 matrices have 5-9 nonzeros).
-template <int K, int UNROLL = 8>
+// A plain dependent loop on purpose: fetching 2-8 nonzeros per trip (more
+// loads in flight per thread) costs registers, and these kernels are bound by
+// occupancy x memory latency -- every batched variant measured slower
+// (profiles/r1_experiments.md).
+template <int K>
 __device__ __forceinline__ void row_product(int p0, int p1, const int *__restrict__ indices,
                                             const double *__restrict__ v0,
                                             const double *__restrict__ v1, const double *x,
                                             int ld, unsigned c, double2 &s0, double2 &s1) {
-    if (UNROLL == 0) {  // plain dependent loop
-        for (int p = p0; p < p1; ++p) {
-            int jj = __ldg(indices + p);
-            double2 xx = ldv2(x + (size_t)jj * ld + c);
-            double b0 = __ldg(v0 + p);
-            s0.x = fma(b0, xx.x, s0.x);
-            s0.y = fma(b0, xx.y, s0.y);
-            if (K == 2) {
-                double b1 = __ldg(v1 + p);
-                s1.x = fma(b1, xx.x, s1.x);
-                s1.y = fma(b1, xx.y, s1.y);
-            }
-        }
-        return;
-    }
-    constexpr int U = UNROLL > 0 ? UNROLL : 1;
-    int j[U];
-    double a0[U], a1[U];
-    double2 xv[U];
-    const int len = p1 - p0;
-#pragma unroll
-    for (int q = 0; q < UNROLL; ++q) {
-        if (q < len) {
-            j[q] = __ldg(indices + p0 + q);
-            a0[q] = __ldg(v0 + p0 + q);
-            if (K == 2) a1[q] = __ldg(v1 + p0 + q);
-        }
-    }
-#pragma unroll
-    for (int q = 0; q < UNROLL; ++q)
-        if (q < len) xv[q] = ldv2(x + (size_t)j[q] * ld + c);
-#pragma unroll
-    for (int q = 0; q < UNROLL; ++q) {
-        if (q < len) {
-            s0.x = fma(a0[q], xv[q].x, s0.x);
-            s0.y = fma(a0[q], xv[q].y, s0.y);
-            if (K == 2) {
-                s1.x = fma(a1[q], xv[q].x, s1.x);
-                s1.y = fma(a1[q], xv[q].y, s1.y);
-            }
-        }
-    }
-    for (int p = p0 + UNROLL; p < p1; ++p) {
-        int jj = __ldg(indices + p);
-        double2 xx = ldv2(x + (size_t)jj * ld + c);
-        double b0 = __ldg(v0 + p);
-        s0.x = fma(b0, xx.x, s0.x);
-        s0.y = fma(b0, xx.y, s0.y);
+    for (int p = p0; p < p1; ++p) {
+        int j = __ldg(indices + p);
+        double2 xv = ldv2(x + (size_t)j * ld + c);
+        double a0 = __ldg(v0 + p);
+        s0.x = fma(a0, xv.x, s0.x);
+        s0.y = fma(a0, xv.y, s0.y);
         if (K == 2) {
-            double b1 = __ldg(v1 + p);
-            s1.x = fma(b1, xx.x, s1.x);
-            s1.y = fma(b1, xx.y, s1.y);
+            double a1 = __ldg(v1 + p);
+            s1.x = fma(a1, xv.x, s1.x);
+            s1.y = fma(a1, xv.y, s1.y);
         }
     }
 }

@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(256)
         unsigned c = (k - i * ld2) * 2u;
         int p0 = __ldg(indptr + i), p1 = __ldg(indptr + i + 1);
         double2 s0 = make_double2(0.0, 0.0), s1 = make_double2(0.0, 0.0);
-        row_product<K, 0>(p0, p1, indices, vals0, vals1, x, ld, c, s0, s1);
+        row_product<K>(p0, p1, indices, vals0, vals1, x, ld, c, s0, s1);
         if (K == 2) {
             double2 c0 = ldg2(coef0 + c), c1 = ldg2(coef1 + c);
             s0.x = fma(c0.x, s0.x, c1.x * s1.x);
@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(256)
         unsigned c = (k - i * ld2) * 2u;
         int p0 = __ldg(indptr + i), p1 = __ldg(indptr + i + 1);
         double2 s0 = make_double2(0.0, 0.0), s1 = make_double2(0.0, 0.0);
-        row_product<2, 0>(p0, p1, indices, vals0, vals1, x, ld, c, s0, s1);
+        row_product<2>(p0, p1, indices, vals0, vals1, x, ld, c, s0, s1);
         size_t o = (size_t)i * ld + c;
         stv2(y0 + o, s0);
         stv2(y1 + o, s1);

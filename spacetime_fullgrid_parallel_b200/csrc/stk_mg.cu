@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(256, 8)
                 }
             }
         } else {
-            row_product<K, 0>(p0, p1, indices, v0, v1, u, ld, c, s0, s1);
+            row_product<K>(p0, p1, indices, v0, v1, u, ld, c, s0, s1);
         }
         double2 diag;
         if (K == 2) {

@@ -22,7 +22,9 @@ def PCG(T, P, b, w0=None, kmax=100000, eps=1e-6, callback=None):
     iters = 0
     if b.dot(b) == 0:
         return w, iters
-    r = b - T @ w
+    # r = b - T w (linalg.py:20).  From the zero start the operator is linear in
+    # w, so T w is exactly zero and the apply is skipped.
+    r = b.copy() if w0 is None else b - T @ w
     p = P @ r
     abs_r = r.dot(p)
     if abs_r < eps * eps:

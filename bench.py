@@ -126,6 +126,54 @@ def cpu_iteration_factory(threads):
     return step, prob.N * prob.M
 
 
+# ---- the CPU arm with one PROCESS per time slab (the reference's mpirun -np P)
+_worker_oracle = None
+
+
+def _worker_init():
+    global _worker_oracle
+    from oracle import restate
+    from spacetime_fullgrid_parallel_b200.assembly import SquareProblem
+    _worker_oracle = restate.HeatEqOracle(SquareProblem(SAMPLE_JS, SAMPLE_JT))
+
+
+def _worker_S(TX_slab):
+    return _worker_oracle.S_slab(TX_slab)
+
+
+def _worker_P(X_slab, levels_slab):
+    return _worker_oracle.P_slab(X_slab, levels_slab)
+
+
+def cpu_iteration_factory_mp(procs):
+    """Same work as cpu_iteration_factory, slabs of time slices farmed out to
+    `procs` worker processes; the time stencils and the wavelet transforms
+    (1 % of the work) stay in the parent.  Returns (fn, dofs, pool)."""
+    import multiprocessing as mp
+    from oracle import restate
+    from spacetime_fullgrid_parallel_b200.assembly import SquareProblem
+    prob = SquareProblem(SAMPLE_JS, SAMPLE_JT)
+    orc = restate.HeatEqOracle(prob)
+    procs = max(1, min(procs, prob.N))
+    pool = mp.get_context('spawn').Pool(procs, initializer=_worker_init)
+    slabs = restate.slab_bounds(prob.N, procs)
+    X = np.random.RandomState(128).rand(prob.N, prob.M)
+
+    def step():
+        Y = orc.W(X)
+        TX = [restate.apply_time(T, Y) for T, _ in orc.terms]
+        parts = pool.starmap(_worker_S, [([tx[a:b] for tx in TX], )
+                                         for a, b in slabs])
+        t = orc.WT(np.concatenate(parts, axis=0))
+        parts = pool.starmap(_worker_P, [(X[a:b], orc.levels[a:b])
+                                         for a, b in slabs])
+        z = np.concatenate(parts, axis=0)
+        return float(X.reshape(-1) @ t.reshape(-1)) + float(
+            X.reshape(-1) @ z.reshape(-1))
+
+    return step, prob.N * prob.M, pool, procs
+
+
 def cpu_baseline(threads=1, min_seconds=10.0):
     step, dofs = cpu_iteration_factory(threads)
     step()  # warm-up (builds nothing lazily, but pages the matrices in)
@@ -150,18 +198,19 @@ def cpu_baseline(threads=1, min_seconds=10.0):
 def run_reference(args):
     """--impl reference: the reference algorithm on the host cores (oracle
     port -- the reference itself is Python + NGSolve/PETSc/MPI and cannot run
-    on the box), all host threads, same metric/unit/config."""
+    on the box), one worker process per time slab on all host cores (its
+    mpirun -np P decomposition), same metric/unit/config."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
-    step, dofs = cpu_iteration_factory(threads)
+    step, dofs, pool, threads = cpu_iteration_factory_mp(os.cpu_count() or 1)
     for _ in range(max(args.warmup, 1)):
         step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step()
     el = time.perf_counter() - t0
+    pool.close()
     ms = el / args.steps * 1e3
     val = dofs / (ms * 1e-3)
     line = {
@@ -177,8 +226,9 @@ def run_reference(args):
             'value': val, 'unit': 'DoF-applies/s', 'cores': threads,
             'kind': 'port',
             'sample': ('each step = one PCG iteration\'s operator applies of '
-                       'the oracle at J_time=%d J_space=%d (%d dofs)' %
-                       (SAMPLE_JT, SAMPLE_JS, dofs))
+                       'the oracle at J_time=%d J_space=%d (%d dofs), time '
+                       'slabs on %d worker processes' %
+                       (SAMPLE_JT, SAMPLE_JS, dofs, threads))
         },
         'e2e': {'value': val, 'unit': 'DoF-applies/s', 'h2d_bytes_per_step': 0,
                 'd2h_bytes_per_step': 0},

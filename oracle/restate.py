@@ -288,18 +288,30 @@ class HeatEqOracle:
             parts = list(pool.map(lambda ab: fn(*ab), slabs))
         return np.concatenate(parts, axis=0)
 
+    def S_slab(self, TX_slab):
+        """The space chains of the five terms on one slab of slices, given the
+        slab of each time-applied vector (what one MPI rank does after the
+        halo exchange, mpi_kron.py:214-219)."""
+        out = np.zeros_like(TX_slab[0])
+        for (T, op), tx in zip(self.terms, TX_slab):
+            out += apply_space(op, np.ascontiguousarray(tx))
+        return out
+
+    def P_slab(self, X_slab, levels_slab):
+        """Block-diagonal preconditioner on one slab (mpi_kron.py:122-132)."""
+        out = np.empty_like(X_slab)
+        for j in np.unique(levels_slab):
+            sel = np.nonzero(levels_slab == j)[0]
+            C = self.C[j]
+            out[sel] = C(apply_space(self.prob.A_x, C(X_slab[sel])))
+        return out
+
     def S(self, X):
         """SumMPI over the five Kronecker terms (mpi_kron.py:77-90): the time
         stencils on the whole vector, the space chains slab by slab."""
         TX = [apply_time(T, X) for T, _ in self.terms]
-
-        def slab(a, b):
-            out = np.zeros_like(X[a:b])
-            for (T, op), tx in zip(self.terms, TX):
-                out += apply_space(op, np.ascontiguousarray(tx[a:b]))
-            return out
-
-        return self._parallel(slab, X.shape[0])
+        return self._parallel(
+            lambda a, b: self.S_slab([tx[a:b] for tx in TX]), X.shape[0])
 
     def WT_S_W(self, X):
         return self.WT(self.S(self.W(X)))  # mpi_kron.py:101-110
@@ -307,16 +319,8 @@ class HeatEqOracle:
     def P(self, X):
         """Block diagonal in time: slice t gets C_j A_x C_j with j = level of
         wavelet t (mpi_kron.py:122-132, heateq_mpi.py:159-162,183-184)."""
-        def slab(a, b):
-            out = np.empty_like(X[a:b])
-            lv = self.levels[a:b]
-            for j in np.unique(lv):
-                sel = np.nonzero(lv == j)[0]
-                C = self.C[j]
-                out[sel] = C(apply_space(self.prob.A_x, C(X[a:b][sel])))
-            return out
-
-        return self._parallel(slab, X.shape[0])
+        return self._parallel(
+            lambda a, b: self.P_slab(X[a:b], self.levels[a:b]), X.shape[0])
 
     def solve(self, **kw):
         return pcg(self.WT_S_W, self.P, self.rhs, **kw)

@@ -39,7 +39,7 @@ import numpy as np  # noqa: E402
 
 WORKLOAD = ('BASELINE.json configs[3]: full preconditioned Schur-complement '
             'PCG solve, J_time=%d J_space=%d square')
-SAMPLE_JT, SAMPLE_JS = 5, 6  # CPU sample: 33 x 16,129 = 532,257 dofs
+SAMPLE_JT, SAMPLE_JS = 5, 7  # CPU sample: 33 x 65,025 = 2,145,825 dofs
 
 
 def peaks():

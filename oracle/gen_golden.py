@@ -25,7 +25,8 @@ from oracle import ref_harness  # noqa: E402
 
 ref_harness.activate()
 
-from spacetime_fullgrid_parallel_b200.assembly import SquareProblem  # noqa: E402
+from spacetime_fullgrid_parallel_b200.assembly import (CubeProblem,  # noqa: E402
+                                                       SquareProblem)
 
 GOLDEN = os.path.join(os.path.dirname(HERE), 'tests', 'golden')
 SEED = 128  # heateq_mpi_timing.py:82
@@ -110,8 +111,9 @@ def sqrt_(x):
 
 
 def _graph_rank(args):
-    Jt, Js, mode, store = args
-    prob = SquareProblem(Js, Jt)
+    Jt, Js, mode, store = args[:4]
+    prob = (CubeProblem if len(args) > 4 and args[4] == 'cube' else
+            SquareProblem)(Js, Jt)
     with contextlib.redirect_stdout(io.StringIO()):
         return graph_outputs(prob, mode, store_solution=store)
 
@@ -151,6 +153,28 @@ def gen_graph():
     np.savez_compressed(os.path.join(GOLDEN, 'graph.npz'), **out)
 
 
+def gen_cube():
+    """problem='cube' (problem.py:21-32, heateq_mpi_test.py:209-243): the
+    reference classes on the Kuhn-triangulation matrices of assembly.py."""
+    from mpi4py import MPI
+    from source.multigrid import MultiGrid
+    out = {}
+    for Jt, Js, mode, P in ((2, 1, 'original', 1), (2, 2, 'composite', 1),
+                            (3, 2, 'composite', 2)):
+        args = (Jt, Js, mode, True, 'cube')
+        res = _graph_rank(args) if P == 1 else merge(
+            MPI.launch(P, _graph_rank, args))
+        tag = 'cube_Jt%d_Js%d_%s_P%d' % (Jt, Js, mode, P)
+        print(tag, 'iters', res['iters'], 'norm_u', res['norm_u'])
+        for k, v in res.items():
+            out['%s__%s' % (tag, k)] = v
+    prob = CubeProblem(2, 1)
+    B = rand((prob.M, 3), seed=31)
+    mg = MultiGrid(prob.Cinv_j[1], prob.hierarchy, smoothsteps=3, vcycles=2)
+    out['cube_C1B_J2'] = np.stack([mg @ B[:, k] for k in range(3)], axis=1)
+    np.savez_compressed(os.path.join(GOLDEN, 'cube.npz'), **out)
+
+
 def gen_lanczos():
     from source.lanczos import Lanczos
     prob = SquareProblem(2, 3)
@@ -165,7 +189,11 @@ def gen_lanczos():
 
 if __name__ == '__main__':
     os.makedirs(GOLDEN, exist_ok=True)
+    if 'cube' in sys.argv[1:]:  # python -m oracle.gen_golden cube
+        gen_cube()
+        sys.exit(0)
     gen_wavelets()
     gen_multigrid()
     gen_lanczos()
     gen_graph()
+    gen_cube()

@@ -219,15 +219,177 @@ class SquareMeshHierarchy:
         return out
 
 
+# ----------------------------------------------------------------------------
+# space direction, 3-D: uniformly refined Kuhn (Freudenthal) triangulation of
+# the unit cube (problem='cube', problem.py:21-32, mesh.py:33-43)
+# ----------------------------------------------------------------------------
+_KUHN_PERMS = [(0, 1, 2), (0, 2, 1), (1, 0, 2), (1, 2, 0), (2, 0, 1), (2, 1, 0)]
+# parity classes of the new vertices of a level = directions of the Kuhn edges
+# whose midpoints they are; (dx, dy, dz)
+_CUBE_CLASSES = [(1, 0, 0), (0, 1, 0), (0, 0, 1), (1, 1, 0), (1, 0, 1),
+                 (0, 1, 1), (1, 1, 1)]
+
+
+def cube_dof_numbering(J_space, order='class', seed=0):
+    """Hierarchical numbering of the interior vertices of the level-J_space
+    grid of the unit cube; `dof` is indexed [z, y, x] in finest-grid
+    coordinates, -1 on the boundary (3-D analogue of square_dof_numbering)."""
+    n = 2**(J_space + 1)
+    dof = np.full((n + 1, n + 1, n + 1), -1, dtype=np.int64)
+    nverts, counter = [], 0
+    rng = np.random.RandomState(seed)
+    for j in range(J_space + 1):
+        s = 2**(J_space - j)
+        nj = 2**(j + 1)
+        r = np.arange(1, nj)
+        Z, Y, X = [a.reshape(-1) for a in np.meshgrid(r, r, r, indexing='ij')]
+        if j == 0:
+            groups = [np.ones(len(X), dtype=bool)]
+        else:
+            px, py, pz = X % 2, Y % 2, Z % 2
+            if order == 'class':
+                groups = [(px == a) & (py == b) & (pz == c)
+                          for a, b, c in _CUBE_CLASSES]
+            else:
+                groups = [(px + py + pz) > 0]
+        for g in groups:
+            idx = np.nonzero(g)[0]
+            if order == 'random':
+                idx = rng.permutation(idx)
+            dof[Z[idx] * s, Y[idx] * s, X[idx] * s] = counter + np.arange(
+                len(idx))
+            counter += len(idx)
+        nverts.append(counter)
+    assert counter == (n - 1)**3
+    return dof, nverts
+
+
+def _assemble_p1_3d(nj, vertex_dof, n_dofs, kind):
+    """P1 mass / stiffness matrix on the Kuhn triangulation with nj cells per
+    side (six tetrahedra per cell, all sharing the cell's main diagonal),
+    restricted to the free dofs; generic element assembly vectorised over the
+    tetrahedra (ngsolve_helper.py:38-46)."""
+    h = 1.0 / nj
+    r = np.arange(nj)
+    cz, cy, cx = [a.reshape(-1) for a in np.meshgrid(r, r, r, indexing='ij')]
+    base = np.stack([cx, cy, cz], axis=1)  # (ncell, 3) as (x, y, z)
+    eye = np.eye(3, dtype=np.int64)
+    verts = []  # (ntet, 4, 3) integer vertex coordinates
+    for perm in _KUHN_PERMS:
+        v = [base]
+        for k in perm:
+            v.append(v[-1] + eye[k])
+        verts.append(np.stack(v, axis=1))
+    verts = np.concatenate(verts, axis=0)
+    P = verts * h
+    E = P[:, 1:, :] - P[:, :1, :]  # edge matrix rows = v_k - v_0
+    det = np.linalg.det(E)
+    vol = np.abs(det) / 6.0
+    if kind == 'mass':
+        loc = (vol / 20.0)[:, None, None] * (np.ones((4, 4)) + np.eye(4))
+    else:
+        # gradients of the barycentric functions: rows of inv(E) for 1..3,
+        # minus their sum for 0
+        Einv = np.linalg.inv(E)  # (ntet, 3, 3): columns = grad phi_k, k=1..3
+        g = np.transpose(Einv, (0, 2, 1))  # (ntet, 3 funcs, 3 comps)
+        g0 = -g.sum(axis=1, keepdims=True)
+        G = np.concatenate([g0, g], axis=1)  # (ntet, 4, 3)
+        loc = vol[:, None, None] * np.einsum('tac,tbc->tab', G, G)
+    d = vertex_dof[verts[:, :, 2], verts[:, :, 1], verts[:, :, 0]]  # (ntet, 4)
+    rows = np.repeat(d[:, :, None], 4, axis=2).reshape(-1)
+    cols = np.repeat(d[:, None, :], 4, axis=1).reshape(-1)
+    vals = loc.reshape(-1)
+    keep = (rows >= 0) & (cols >= 0)
+    mat = sp.coo_matrix((vals[keep], (rows[keep], cols[keep])),
+                        shape=(n_dofs, n_dofs)).tocsr()
+    # exact zeros of the stiffness matrix (orthogonal gradients) appear as
+    # round-off of size 1e-17: drop them as NGSolve's eliminate_zeros would
+    mat.data[np.abs(mat.data) < 1e-13 * np.abs(mat.data).max()] = 0.0
+    mat.eliminate_zeros()
+    mat.sort_indices()
+    return mat
+
+
+def _prolongation_3d(dof_f, nf_dofs, nc_dofs, njf):
+    """P: level j -> j+1 on the cube (multigrid.py:39-59): new vertices are
+    midpoints of Kuhn edges, their parents the two end points."""
+    r = np.arange(1, njf)
+    Z, Y, X = [a.reshape(-1) for a in np.meshgrid(r, r, r, indexing='ij')]
+    px, py, pz = X % 2, Y % 2, Z % 2
+    me = dof_f[Z, Y, X]
+    old = (px + py + pz) == 0
+    rows, cols, vals = [me[old]], [me[old]], [np.ones(old.sum())]
+    for dx, dy, dz in _CUBE_CLASSES:
+        sel = (px == dx) & (py == dy) & (pz == dz)
+        for sgn in (-1, 1):
+            par = dof_f[Z[sel] + sgn * dz, Y[sel] + sgn * dy, X[sel] + sgn * dx]
+            ok = par >= 0
+            rows.append(me[sel][ok])
+            cols.append(par[ok])
+            vals.append(np.full(ok.sum(), 0.5))
+    rows, cols, vals = map(np.concatenate, (rows, cols, vals))
+    assert cols.max() < nc_dofs
+    P = sp.coo_matrix((vals, (rows, cols)), shape=(nf_dofs, nc_dofs)).tocsr()
+    P.sort_indices()
+    return P
+
+
+class CubeMeshHierarchy:
+    """3-D counterpart of SquareMeshHierarchy: level j is the Kuhn
+    triangulation of the 2^(j+1) x 2^(j+1) x 2^(j+1) grid, (2^(j+1)-1)^3
+    interior vertices, hierarchical numbering.  With order='class' the eight
+    parity classes of a level are independent sets of the 15-point mass-matrix
+    graph, i.e. lexicographic Gauss-Seidel is an 8-wavefront sweep."""
+    def __init__(self, J_space, order='class', seed=0):
+        self.J = J_space
+        self.order = order
+        self.dof, self.nverts = cube_dof_numbering(J_space, order, seed)
+        self.shared_comm = None
+        self.P_mats = []
+        for j in range(J_space):
+            s = 2**(J_space - (j + 1))
+            self.P_mats.append(
+                _prolongation_3d(self.dof[::s, ::s, ::s], self.nverts[j + 1],
+                                 self.nverts[j], 2**(j + 2)))
+        self.R_mats = [P.T.tocsr() for P in self.P_mats]
+        for R in self.R_mats:
+            R.sort_indices()
+
+    def level_dof(self, j):
+        s = 2**(self.J - j)
+        return self.dof[::s, ::s, ::s]
+
+    def assemble(self, kind, j=None):
+        j = self.J if j is None else j
+        return _assemble_p1_3d(2**(j + 1), self.level_dof(j), self.nverts[j],
+                               kind)
+
+    def nodal_values(self, fn):
+        n = 2**(self.J + 1)
+        Z, Y, X = np.nonzero(self.dof >= 0)
+        out = np.empty(self.nverts[-1])
+        out[self.dof[Z, Y, X]] = fn(X / n, Y / n, Z / n)
+        return out
+
+
 class SquareProblem:
     """Everything heateq_mpi.py:63-104 obtains from NGSolve for
     problem='square' (problem.py:7-18): u(t,x,y)=exp(-2pi^2 t)sin(pi x)sin(pi y).
     """
+    dim = 2
+
+    def _mesh(self, J_space, order, seed):
+        return SquareMeshHierarchy(J_space, order, seed)
+
+    def _u0(self):
+        return self.hierarchy.nodal_values(
+            lambda x, y: np.sin(np.pi * x) * np.sin(np.pi * y))
+
     def __init__(self, J_space, J_time=None, alpha=0.3, order='class', seed=0):
         if J_time is None:
             J_time = J_space
         self.J_space, self.J_time, self.alpha = J_space, J_time, alpha
-        self.hierarchy = SquareMeshHierarchy(J_space, order, seed)
+        self.hierarchy = self._mesh(J_space, order, seed)
         self.A_t, self.L_t, self.M_t, self.G_t, self.u0_t = time_matrices(
             J_time)
         self.M_x = self.hierarchy.assemble('mass')
@@ -237,8 +399,7 @@ class SquareProblem:
         # u0_x = int u0 phi_i, with u0 replaced by its nodal interpolant
         # (NGSolve's quadrature is not observable).  u0
         # vanishes on the boundary, so the free-dof mass matrix suffices.
-        u0 = self.hierarchy.nodal_values(
-            lambda x, y: np.sin(np.pi * x) * np.sin(np.pi * y))
+        u0 = self._u0()
         self.u0_x = self.M_x @ u0
         self._Cinv_j = None
 
@@ -252,3 +413,17 @@ class SquareProblem:
                 for j in range(self.J_time + 1)
             ]
         return self._Cinv_j
+
+
+class CubeProblem(SquareProblem):
+    """problem='cube' (problem.py:21-32): u = exp(-3 pi^2 t) sin(pi x) sin(pi y)
+    sin(pi z) on the unit cube, Kuhn triangulation."""
+    dim = 3
+
+    def _mesh(self, J_space, order, seed):
+        return CubeMeshHierarchy(J_space, order, seed)
+
+    def _u0(self):
+        return self.hierarchy.nodal_values(
+            lambda x, y, z: np.sin(np.pi * x) * np.sin(np.pi * y) * np.sin(
+                np.pi * z))

@@ -108,12 +108,14 @@ class HeatEquationMPI:
 
         # ---- host assembly (the NGSolve block, heateq_mpi.py:63-104) ----
         if isinstance(problem, str):
-            if problem != 'square':
+            from .assembly import CubeProblem, SquareProblem
+            makers = {'square': SquareProblem, 'cube': CubeProblem}
+            if problem not in makers:
                 raise NotImplementedError(
-                    "problem %r: only 'square' has a host assembler here; "
-                    'pass an assembled problem object instead' % problem)
-            from .assembly import SquareProblem
-            problem = SquareProblem(J_space, J_time, alpha=alpha, order=order)
+                    "problem %r: 'square' and 'cube' have host assemblers here;"
+                    ' pass an assembled problem object instead' % problem)
+            problem = makers[problem](J_space, J_time, alpha=alpha,
+                                      order=order)
         prob = self.problem = problem
         self.N, self.M = prob.N, prob.M
         self.mem_after_ngsolve = mem()

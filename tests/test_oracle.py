@@ -6,7 +6,7 @@ import scipy.sparse as sp
 
 from conftest import rand, rel
 from oracle import restate as orc
-from spacetime_fullgrid_parallel_b200.assembly import SquareProblem
+from spacetime_fullgrid_parallel_b200.assembly import CubeProblem, SquareProblem
 
 
 def test_slab_bounds():
@@ -155,3 +155,45 @@ def test_lanczos_golden(golden):
         rmax, rmin, rits = g['lanczos_mgA_J%d' % Js]
         assert abs(lmax - rmax) < 1e-10 * rmax and abs(lmin - rmin) < 1e-10 * rmin
         assert its == int(rits)
+
+
+def test_cube_golden(golden):
+    """problem='cube' (problem.py:21-32): oracle vs the reference classes on
+    the Kuhn-triangulation matrices (tests/golden/cube.npz)."""
+    g = golden['cube']
+    for Jt, Js, inter, tag in ((2, 1, False, 'cube_Jt2_Js1_original_P1'),
+                               (2, 2, True, 'cube_Jt2_Js2_composite_P1'),
+                               (3, 2, True, 'cube_Jt3_Js2_composite_P2')):
+        prob = CubeProblem(Js, Jt)
+        o = orc.HeatEqOracle(prob, interleaved=inter)
+        X = rand((prob.N, prob.M))
+        for name in ('W', 'S', 'WT', 'P', 'WT_S_W'):
+            assert rel(getattr(o, name)(X), g['%s__%s' % (tag, name)]) < 1e-13
+        w, iters = o.solve()
+        assert iters == int(g[tag + '__iters'])
+        assert rel(w, g[tag + '__w']) < 1e-10
+    prob = CubeProblem(2, 1)
+    B = rand((prob.M, 3), seed=31)
+    mg = orc.MultiGridOracle(prob.Cinv_j[1], prob.hierarchy.P_mats, 3, 2)
+    assert rel(mg @ B, g['cube_C1B_J2']) < 1e-13
+
+
+def test_cube_assembler():
+    """Galerkin identity on the Kuhn hierarchy (multigrid_test.py:14-37 covers
+    the cube), stencil sizes, and a Poisson solve against the exact solution."""
+    import scipy.sparse.linalg as sla
+    prob = CubeProblem(2, 1)
+    h = prob.hierarchy
+    assert prob.M == 7**3
+    assert prob.M_x.getnnz(axis=1).max() == 15
+    assert prob.A_x.getnnz(axis=1).max() == 7
+    for kind in ('stiff', 'mass'):
+        A = h.assemble(kind)
+        for j in reversed(range(h.J)):
+            A = (h.R_mats[j] @ A @ h.P_mats[j]).tocsr()
+            ref = h.assemble(kind, j)
+            assert abs(A - ref).max() < 1e-13 * abs(ref).max()
+    prob = CubeProblem(3, 1)
+    u_ex = prob._u0()
+    u = sla.spsolve(prob.A_x.tocsc(), prob.M_x @ (3 * np.pi**2 * u_ex))
+    assert rel(u, u_ex) < 0.03

@@ -113,24 +113,26 @@ int stk_time_apply(int M, int nrows_t, int nnz, const int *indptr,
 /* Two-input form, y = alpha * [Ta Tb] [x0; x1] + beta * y: column c of the
  * stacked CSR addresses x0 (c < ncols_local), x1 (c < 2 ncols_local), the
  * n_halo0 halo slices of x0, then the halo slices of x1.  One pass computes
- * (A_t (x) I) Mx + (L_t (x) I) Ax of heateq_mpi.py:166-178. */
+ * (A_t (x) I) Mx + (L_t (x) I) Ax of heateq_mpi.py:166-178.  y has pitch ldy
+ * and wy <= ldy columns are written (two results side by side in one block
+ * of pitch 2*ld go through the multigrid solve together). */
 int stk_time_apply2(int M, int nrows_t, const int *indptr, const int *indices,
                     const double *vals, const double *x0, const double *x1,
                     int ldx, int ncols_local, const double *xh0, int n_halo0,
                     const double *xh1, double alpha, double beta, double *y,
-                    int ldy, void *stream);
+                    int ldy, int wy, void *stream);
 /* Two matrices on one sparsity pattern (M_x and A_x, heateq_mpi.py:166-178):
  * split: y0 = A0 x, y1 = A1 x (x and the pattern read once);
- * pair : y = alpha * (A0 x0 + A1 x1) + beta * z. */
+ * pair : y = alpha * (A0 x0 + A1 x1) + beta * z  (x0, x1 of pitch ldx). */
 int stk_space_spmm_split(int nrows, const int *indptr, const int *indices,
                          const double *vals0, const double *vals1,
                          const double *x, double *y0, double *y1, int ld,
                          void *stream);
 int stk_space_spmm_pair(int nrows, const int *indptr, const int *indices,
                         const double *vals0, const double *vals1,
-                        const double *x0, const double *x1, double alpha,
-                        double beta, const double *z, double *y, int ld,
-                        void *stream);
+                        const double *x0, const double *x1, int ldx,
+                        double alpha, double beta, const double *z, double *y,
+                        int ld, void *stream);
 /* out[h*M + i] = x[i*ld + tidx[h]]   (pack time slices for a send). */
 int stk_pack_slices(const double *x, int ld, int M, const int *tidx, int n,
                     double *out, void *stream);

@@ -38,13 +38,14 @@ SIGNATURES = {
     ]),
     'stk_time_apply2': (_int, [
         _int, _int, _vp, _vp, _vp, _vp, _vp, _int, _int, _vp, _int, _vp, _dbl,
-        _dbl, _vp, _int, _vp
+        _dbl, _vp, _int, _int, _vp
     ]),
     'stk_space_spmm_split': (_int, [
         _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _vp
     ]),
     'stk_space_spmm_pair': (_int, [
-        _int, _vp, _vp, _vp, _vp, _vp, _vp, _dbl, _dbl, _vp, _vp, _int, _vp
+        _int, _vp, _vp, _vp, _vp, _vp, _vp, _int, _dbl, _dbl, _vp, _vp, _int,
+        _vp
     ]),
     'stk_pack_slices': (_int, [_vp, _int, _int, _vp, _int, _vp, _vp]),
     'stk_unpack_slices': (_int,

@@ -134,8 +134,8 @@ __global__ void __launch_bounds__(256)
                   const int *__restrict__ indices, const double *__restrict__ vals,
                   const double *__restrict__ x0, const double *__restrict__ x1, int ldx, int n,
                   const double *__restrict__ xh0, int nh0, const double *__restrict__ xh1,
-                  double alpha, double beta, double *__restrict__ y, int ldy) {
-    const unsigned ld2 = (unsigned)ldy / 2u;
+                  double alpha, double beta, double *__restrict__ y, int ldy, int wy) {
+    const unsigned ld2 = (unsigned)wy / 2u;  // columns written per row (<= pitch ldy)
     const unsigned total = (unsigned)M * ld2;
     const unsigned stride = gridDim.x * 256u;
     for (unsigned k = blockIdx.x * 256u + threadIdx.x; k < total; k += stride) {
@@ -185,8 +185,9 @@ template <bool HAS_Z>
 __global__ void __launch_bounds__(256)
     k_space_spmm_pair(int nrows, const int *__restrict__ indptr, const int *__restrict__ indices,
                       const double *__restrict__ vals0, const double *__restrict__ vals1,
-                      const double *__restrict__ x0, const double *__restrict__ x1, double alpha,
-                      double beta, const double *z, double *y, int ld, unsigned ld2) {
+                      const double *__restrict__ x0, const double *__restrict__ x1, int ldx,
+                      double alpha, double beta, const double *z, double *y, int ld,
+                      unsigned ld2) {
     const unsigned total = (unsigned)nrows * ld2;
     const unsigned stride = gridDim.x * 256u;
     for (unsigned k = blockIdx.x * 256u + threadIdx.x; k < total; k += stride) {
@@ -195,7 +196,7 @@ __global__ void __launch_bounds__(256)
         int p1 = __ldg(indptr + i + 1);
         double2 s = make_double2(0.0, 0.0);
         for (int p = __ldg(indptr + i); p < p1; ++p) {
-            size_t off = (size_t)__ldg(indices + p) * ld + c;
+            size_t off = (size_t)__ldg(indices + p) * ldx + c;
             double2 a = ldv2(x0 + off), b = ldv2(x1 + off);
             double m = __ldg(vals0 + p), w = __ldg(vals1 + p);
             s.x = fma(m, a.x, fma(w, b.x, s.x));
@@ -410,21 +411,22 @@ int stk_time_apply(int M, int nrows_t, int nnz, const int *indptr, const int *in
 int stk_time_apply2(int M, int nrows_t, const int *indptr, const int *indices,
                     const double *vals, const double *x0, const double *x1, int ldx,
                     int ncols_local, const double *xh0, int n_halo0, const double *xh1,
-                    double alpha, double beta, double *y, int ldy, void *stream) {
+                    double alpha, double beta, double *y, int ldy, int wy, void *stream) {
     if (x0 == y || x1 == y) return fail(-1, "stk_time_apply2: inputs must not alias y");
-    if (nrows_t > ldy || (ldy & 1)) return fail(-1, "stk_time_apply2: bad pitch of y");
+    if (nrows_t > wy || wy > ldy || (ldy & 1) || (wy & 1))
+        return fail(-1, "stk_time_apply2: need nrows_t <= wy <= ldy, both even");
     if (M == 0) return 0;
-    int64_t work = (int64_t)M * (ldy / 2);
+    int64_t work = (int64_t)M * (wy / 2);
     if (work >= (1ll << 32)) return fail(-2, "stk_time_apply2: block too large");
     cudaStream_t s = as_stream(stream);
     if (beta != 0.0)
         k_time_apply2<true><<<resident_grid(k_time_apply2<true>, 256, work), 256, 0, s>>>(
             M, nrows_t, indptr, indices, vals, x0, x1, ldx, ncols_local, xh0, n_halo0, xh1, alpha,
-            beta, y, ldy);
+            beta, y, ldy, wy);
     else
         k_time_apply2<false><<<resident_grid(k_time_apply2<false>, 256, work), 256, 0, s>>>(
             M, nrows_t, indptr, indices, vals, x0, x1, ldx, ncols_local, xh0, n_halo0, xh1, alpha,
-            beta, y, ldy);
+            beta, y, ldy, wy);
     return check_launch("k_time_apply2");
 }
 
@@ -444,9 +446,11 @@ int stk_space_spmm_split(int nrows, const int *indptr, const int *indices, const
 }
 
 int stk_space_spmm_pair(int nrows, const int *indptr, const int *indices, const double *vals0,
-                        const double *vals1, const double *x0, const double *x1, double alpha,
-                        double beta, const double *z, double *y, int ld, void *stream) {
-    if (ld & 3) return fail(-1, "stk_space_spmm_pair: pitch must be a multiple of 4");
+                        const double *vals1, const double *x0, const double *x1, int ldx,
+                        double alpha, double beta, const double *z, double *y, int ld,
+                        void *stream) {
+    if ((ld & 3) || (ldx & 1) || ldx < ld)
+        return fail(-1, "stk_space_spmm_pair: need ld % 4 == 0 and an even ldx >= ld");
     if (x0 == y || x1 == y) return fail(-1, "stk_space_spmm_pair: inputs must not alias y");
     if (beta != 0.0 && !z) return fail(-1, "stk_space_spmm_pair: beta != 0 needs z");
     if (nrows == 0) return 0;
@@ -456,11 +460,11 @@ int stk_space_spmm_pair(int nrows, const int *indptr, const int *indices, const 
     cudaStream_t s = as_stream(stream);
     if (beta != 0.0)
         k_space_spmm_pair<true><<<resident_grid(k_space_spmm_pair<true>, 256, work), 256, 0, s>>>(
-            nrows, indptr, indices, vals0, vals1, x0, x1, alpha, beta, z, y, ld, ld2);
+            nrows, indptr, indices, vals0, vals1, x0, x1, ldx, alpha, beta, z, y, ld, ld2);
     else
         k_space_spmm_pair<false><<<resident_grid(k_space_spmm_pair<false>, 256, work), 256, 0,
-                                   s>>>(nrows, indptr, indices, vals0, vals1, x0, x1, alpha, beta,
-                                        z, y, ld, ld2);
+                                   s>>>(nrows, indptr, indices, vals0, vals1, x0, x1, ldx, alpha,
+                                        beta, z, y, ld, ld2);
     return check_launch("k_space_spmm_pair");
 }
 

@@ -78,15 +78,20 @@ class SchurOperatorMPI(LinearOperatorMPI):
                  for p in self.plans.values())
         mx, ax = vec_in.empty_like(), vec_in.empty_like()
         self.MA.split(vec_in.data, mx.data, ax.data)  # M x and A x, one pass
-        y = torch.empty_like(vec_in.data)
-        z1 = torch.empty_like(vec_in.data)
-        z2 = torch.empty_like(vec_in.data)
+        # the two brackets side by side in one block of pitch 2*ld, so that K
+        # solves for both in ONE batched V-cycle (twice the columns per launch:
+        # what keeps narrow time slabs on many GPUs efficient)
+        ld = vec_in.ld
+        y = torch.empty((vec_in.M, 2 * ld), dtype=torch.float64,
+                        device=vec_in.data.device)
+        z = torch.empty_like(y)
         vec_out._invalidate()
-        self.bracket1.apply(mx, ax, y)  # A_t M x + L_t A x
-        self.K.apply_block(y, z1)
-        self.bracket2.apply(mx, ax, y)  # L_t^T M x + M_t A x
-        self.K.apply_block(y, z2)
-        self.MA.pair(z1, z2, vec_out.data)  # M z1 + A z2
+        self.bracket1.apply(mx, ax, y.data_ptr(), ldy=2 * ld)  # A_t Mx + L_t Ax
+        self.bracket2.apply(mx, ax, y.data_ptr() + 8 * ld,
+                            ldy=2 * ld)  # L_t^T Mx + M_t Ax
+        self.K.apply_block(y, z)
+        self.MA.pair(z.data_ptr(), z.data_ptr() + 8 * ld, vec_out.data,
+                     ldx=2 * ld)  # M z1 + A z2
         self.plans['G'].apply(mx, vec_out.data, 1.0, 1.0)  # + G_t (x) M x
         self.time_communication += sum(
             getattr(p, 'time_communication', 0.0)

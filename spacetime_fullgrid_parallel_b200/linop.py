@@ -101,13 +101,20 @@ class DeviceCSRPair:
                                          ptr(self.vals1), ptr(x), ptr(y0),
                                          ptr(y1), x.shape[1], stream()))
 
-    def pair(self, x0, x1, out, alpha=1.0, beta=0.0, z=None):
-        """out = alpha (mat0 x0 + mat1 x1) + beta z."""
+    def pair(self, x0, x1, out, alpha=1.0, beta=0.0, z=None, ldx=None):
+        """out = alpha (mat0 x0 + mat1 x1) + beta z; x0 / x1 may be device
+        addresses of sub-blocks with pitch ldx."""
+        ld = out.shape[1]
         check(lib().stk_space_spmm_pair(self.shape[0], ptr(self.indptr),
                                         ptr(self.indices), ptr(self.vals0),
-                                        ptr(self.vals1), ptr(x0), ptr(x1),
+                                        ptr(self.vals1), _addr(x0), _addr(x1),
+                                        ld if ldx is None else ldx,
                                         float(alpha), float(beta), ptr(z),
-                                        ptr(out), x0.shape[1], stream()))
+                                        ptr(out), ld, stream()))
+
+
+def _addr(t):
+    return t if isinstance(t, int) else ptr(t)
 
 
 _csr_cache = {}

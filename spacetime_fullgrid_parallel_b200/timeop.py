@@ -203,7 +203,9 @@ class TimeOpPlan2:
         self.local.sort_indices()
         self._dev = None
 
-    def apply(self, va, vb, out_block, alpha=1.0, beta=0.0):
+    def apply(self, va, vb, out_block, alpha=1.0, beta=0.0, ldy=None):
+        """out_block: a device tensor, or a raw device address of a sub-block
+        with pitch ldy (va.ld columns are written)."""
         import torch
         from ._lib import check, lib, ptr, stream
         dev = va.data.device
@@ -220,8 +222,11 @@ class TimeOpPlan2:
                                     ptr(indices), ptr(vals), ptr(va.data),
                                     ptr(vb.data), va.ld, self.a.n_loc,
                                     ptr(ha), self.a.n_halo, ptr(hb),
-                                    float(alpha), float(beta), ptr(out_block),
-                                    va.ld, stream()))
+                                    float(alpha), float(beta),
+                                    out_block if isinstance(out_block, int)
+                                    else ptr(out_block),
+                                    va.ld if ldy is None else ldy, va.ld,
+                                    stream()))
 
 
 def _now():

@@ -78,8 +78,8 @@ def test_space_spmm_family_and_modes(cuda, n_t, M):
                                  ptr(y1), ld, None))
     assert rel(y0.cpu().numpy()[:, :n_t].T, (A0 @ X.T).T) < 1e-14
     assert rel(y1.cpu().numpy()[:, :n_t].T, (A1 @ X.T).T) < 1e-14
-    check(L.stk_space_spmm_pair(M, ptr(ip), ptr(ix), ptr(v0), ptr(v1), ptr(x), ptr(z), 1.5, 0.5,
-                                ptr(y0), ptr(y), ld, None))
+    check(L.stk_space_spmm_pair(M, ptr(ip), ptr(ix), ptr(v0), ptr(v1), ptr(x), ptr(z), ld, 1.5,
+                                0.5, ptr(y0), ptr(y), ld, None))
     ref = 1.5 * ((A0 @ X.T).T + (A1 @ Z.T).T) + 0.5 * (A0 @ X.T).T
     assert rel(y.cpu().numpy()[:, :n_t].T, ref) < 1e-14
     # aliasing is refused, not silently wrong
@@ -143,7 +143,7 @@ def test_time_apply2_and_empty_rows(cuda):
     y = torch.full((M, ld), np.nan, dtype=torch.float64, device='cuda')
     dha, dhb = torch.from_numpy(ha).cuda(), torch.from_numpy(hb).cuda()
     check(L.stk_time_apply2(M, n, ptr(ip), ptr(ix), ptr(iv), ptr(xa), ptr(xb), ld, n, ptr(dha),
-                            2, ptr(dhb), 1.0, 0.0, ptr(y), ld, None))
+                            2, ptr(dhb), 1.0, 0.0, ptr(y), ld, ld, None))
     ref = S @ np.concatenate([Xa, Xb, ha, hb])
     got = y.cpu().numpy()
     assert rel(got[:, :n].T, ref) < 1e-14 and np.all(got[:, n:] == 0.0)

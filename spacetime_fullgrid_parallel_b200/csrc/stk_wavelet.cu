@@ -7,69 +7,82 @@
 
 namespace stk {
 
-// a: current values, b: scratch of the same length (N doubles each).
-// Level j works on the nodes m*S, m = 0..nj (nj = 2^j, S = 2^(J-j)); even m are
-// the hats of level j-1, odd m the wavelets of level j.
-__device__ __forceinline__ void synth_level(double *a, double *b, int J, int j, int lane) {
-    const int S = 1 << (J - j), nj = 1 << j;
-    const double s = exp2(0.5 * j), hs = 0.5 * s;
-    for (int m = lane; m <= nj; m += 32) {
-        double v;
-        if (m & 1) {  // fine[odd] = (c_l + c_r)/2 + s d      (wavelets.py:81-104)
-            v = fma(s, a[m * S], 0.5 * (a[(m - 1) * S] + a[(m + 1) * S]));
-        } else {  // fine[even] = c - s/2 (d_l + d_r); boundary wavelets count twice
-            double dl = a[(m > 0 ? m - 1 : m + 1) * S];
-            double dr = a[(m < nj ? m + 1 : m - 1) * S];
-            v = fma(-hs, dr, fma(-hs, dl, a[m * S]));
-        }
-        b[m * S] = v;
-    }
-    __syncwarp();
-    for (int m = lane; m <= nj; m += 32) a[m * S] = b[m * S];
-    __syncwarp();
-}
-
-__device__ __forceinline__ void analysis_level(double *a, double *b, int J, int j, int lane) {
-    const int S = 1 << (J - j), nj = 1 << j;
-    const double s = exp2(0.5 * j);
-    for (int m = lane; m <= nj; m += 32) {
-        double v;
-        if (m & 1) {  // d = s (od - ev_l/2 - ev_r/2), boundary hats count twice
-            double el = a[(m - 1) * S], er = a[(m + 1) * S];
-            v = a[m * S] - 0.5 * el - 0.5 * er;
-            if (m == 1) v -= 0.5 * el;
-            if (m == nj - 1) v -= 0.5 * er;
-            v *= s;
-        } else {  // c = ev + od_l/2 + od_r/2
-            v = a[m * S];
-            if (m > 0) v = fma(0.5, a[(m - 1) * S], v);
-            if (m < nj) v = fma(0.5, a[(m + 1) * S], v);
-        }
-        b[m * S] = v;
-    }
-    __syncwarp();
-    for (int m = lane; m <= nj; m += 32) a[m * S] = b[m * S];
-    __syncwarp();
-}
-
+// Shared memory per warp (one time column): raw[N] | b0[H] | b1[H] | outb[N],
+// H = 2^(J-1) + 1.  raw is the input column: level j reads its wavelet
+// coefficients (odd nodes) from it.  The hats a level produces are stored
+// COMPACTLY (node m of level j at index m) in b[j & 1], so consecutive lanes
+// touch consecutive words (no bank conflicts, no shifts) and no level copies
+// anything back; the last synthesis level writes straight to global memory,
+// the analysis collects finished coefficients in outb for one coalesced store.
 template <bool TRANSPOSE>
 __global__ void k_wavelet_lift(int M, int J, double *__restrict__ x, int ld) {
     extern __shared__ double smem[];
-    const int N = (1 << J) + 1;
+    const int N = (1 << J) + 1, H = (1 << (J - 1)) + 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wpb = blockDim.x >> 5;
-    double *a = smem + (size_t)warp * 2 * N;
-    double *b = a + N;
+    const int per_warp = N + 2 * H + (TRANSPOSE ? N : 0);
+    double *raw = smem + (size_t)warp * per_warp;
+    double *b0 = raw + N, *b1 = b0 + H;
+    double *outb = b1 + H;
     for (int i = blockIdx.x * wpb + warp; i < M; i += gridDim.x * wpb) {
         double *xi = x + (size_t)i * ld;
-        for (int t = lane; t < N; t += 32) a[t] = xi[t];
+        for (int t = lane; t < N; t += 32) raw[t] = xi[t];
         __syncwarp();
-        if (TRANSPOSE) {
-            for (int j = J; j >= 1; --j) analysis_level(a, b, J, j, lane);
+        if (!TRANSPOSE) {
+            // level j: hats c of level j-1 (compact, from the previous level;
+            // the two level-0 hats are raw[0], raw[N-1]) and wavelets d of
+            // level j (raw, stride 2^(J-j)) -> hats of level j
+            // (wavelets.py:81-104)
+            for (int j = 1; j <= J; ++j) {
+                const int sh = J - j, nj = 1 << j;
+                const double s = exp2(0.5 * j), hs = 0.5 * s;
+                const double *c = (j - 1) & 1 ? b1 : b0;
+                double *dst = j & 1 ? b1 : b0;
+                for (int m = lane; m <= nj; m += 32) {
+                    double v;
+                    if (m & 1) {
+                        double cl = (j == 1) ? raw[0] : c[(m - 1) >> 1];
+                        double cr = (j == 1) ? raw[N - 1] : c[(m + 1) >> 1];
+                        v = fma(s, raw[m << sh], 0.5 * (cl + cr));
+                    } else {
+                        double cm = (j == 1) ? raw[m ? N - 1 : 0] : c[m >> 1];
+                        double dl = raw[(m > 0 ? m - 1 : m + 1) << sh];
+                        double dr = raw[(m < nj ? m + 1 : m - 1) << sh];
+                        v = fma(-hs, dr, fma(-hs, dl, cm));
+                    }
+                    if (j == J) xi[m] = v;
+                    else dst[m] = v;
+                }
+                __syncwarp();
+            }
         } else {
-            for (int j = 1; j <= J; ++j) synth_level(a, b, J, j, lane);
+            // level j (J down to 1): values y of the level-j nodes (compact; the
+            // finest level reads raw) -> hats of level j-1 (compact) and the
+            // finished level-j wavelet coefficients (wavelets.py:120-134)
+            for (int j = J; j >= 1; --j) {
+                const int sh = J - j, nj = 1 << j;
+                const double s = exp2(0.5 * j);
+                const double *y = (j == J) ? raw : ((j + 1) & 1 ? b1 : b0);
+                double *dst = j & 1 ? b1 : b0;
+                for (int m = lane; m <= nj; m += 32) {
+                    if (m & 1) {
+                        double el = y[m - 1], er = y[m + 1];
+                        double v = y[m] - 0.5 * el - 0.5 * er;
+                        if (m == 1) v -= 0.5 * el;
+                        if (m == nj - 1) v -= 0.5 * er;
+                        outb[m << sh] = v * s;
+                    } else {
+                        double v = y[m];
+                        if (m > 0) v = fma(0.5, y[m - 1], v);
+                        if (m < nj) v = fma(0.5, y[m + 1], v);
+                        if (j == 1) outb[m << sh] = v;
+                        else dst[m >> 1] = v;
+                    }
+                }
+                __syncwarp();
+            }
+            for (int t = lane; t < N; t += 32) xi[t] = outb[t];
         }
-        for (int t = lane; t < N; t += 32) xi[t] = a[t];
         __syncwarp();
     }
 }
@@ -83,7 +96,8 @@ extern "C" int stk_wavelet_lift(int M, int J, int transpose, double *x, int ld, 
     const int N = (1 << J) + 1;
     if (ld < N) return fail(-1, "stk_wavelet_lift: pitch smaller than 2^J + 1");
     if (M == 0 || J == 0) return 0;
-    size_t per_warp = sizeof(double) * 2 * (size_t)N;
+    const int H = (1 << (J - 1)) + 1;
+    size_t per_warp = sizeof(double) * ((size_t)N + 2 * H + (transpose ? N : 0));
     int wpb = (int)((200 * 1024) / per_warp);
     if (wpb > 8) wpb = 8;
     if (wpb < 1) return fail(-1, "stk_wavelet_lift: time column does not fit shared memory");

@@ -144,9 +144,10 @@ int stk_unpack_slices(double *x, int ld, int M, const int *tidx, int n,
 /* ---- wavelet transform in time, in-place lifting ------------------------
  * wavelets.py:106-134 (WaveletTransformOp._matmat/_rmatmat, interleaved
  * ordering) for a block holding the whole time axis (n_t = 2^J + 1).
- * transpose = 0: x <- W x (levels 1..J); transpose = 1: x <- W^T x. */
-int stk_wavelet_lift(int M, int J, int transpose, double *x, int ld,
-                     void *stream);
+ * transpose = 0: x <- W src (levels 1..J); transpose = 1: x <- W^T src.
+ * src may be x (in place) or another block of the same pitch. */
+int stk_wavelet_lift(int M, int J, int transpose, const double *src,
+                     double *x, int ld, void *stream);
 
 /* ---- multigrid V-cycle, batched over all time slices --------------------
  * multigrid.py:130-197 (MultiGrid), :100-127 (PETSc MatSOR sweeps).

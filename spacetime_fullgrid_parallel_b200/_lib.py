@@ -50,7 +50,7 @@ SIGNATURES = {
     'stk_pack_slices': (_int, [_vp, _int, _int, _vp, _int, _vp, _vp]),
     'stk_unpack_slices': (_int,
                           [_vp, _int, _int, _vp, _int, _vp, _dbl, _dbl, _vp]),
-    'stk_wavelet_lift': (_int, [_int, _int, _int, _vp, _int, _vp]),
+    'stk_wavelet_lift': (_int, [_int, _int, _int, _vp, _vp, _int, _vp]),
     'stk_mg_create': (_vp, [_int, _int, _int, _int]),
     'stk_mg_destroy': (None, [_vp]),
     'stk_mg_set_level': (_int, [

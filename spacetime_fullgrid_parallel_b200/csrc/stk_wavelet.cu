@@ -15,7 +15,7 @@ namespace stk {
 // anything back; the last synthesis level writes straight to global memory,
 // the analysis collects finished coefficients in outb for one coalesced store.
 template <bool TRANSPOSE>
-__global__ void k_wavelet_lift(int M, int J, double *__restrict__ x, int ld) {
+__global__ void k_wavelet_lift(int M, int J, const double *src, double *x, int ld) {
     extern __shared__ double smem[];
     const int N = (1 << J) + 1, H = (1 << (J - 1)) + 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -26,7 +26,10 @@ __global__ void k_wavelet_lift(int M, int J, double *__restrict__ x, int ld) {
     double *outb = b1 + H;
     for (int i = blockIdx.x * wpb + warp; i < M; i += gridDim.x * wpb) {
         double *xi = x + (size_t)i * ld;
-        for (int t = lane; t < N; t += 32) raw[t] = xi[t];
+        const double *si = src + (size_t)i * ld;
+        for (int t = lane; t < N; t += 32) raw[t] = si[t];
+        if (src != x)  // out of place: the pad columns of the result are zero
+            for (int t = N + lane; t < ld; t += 32) xi[t] = 0.0;
         __syncwarp();
         if (!TRANSPOSE) {
             // level j: hats c of level j-1 (compact, from the previous level;
@@ -91,11 +94,19 @@ __global__ void k_wavelet_lift(int M, int J, double *__restrict__ x, int ld) {
 
 using namespace stk;
 
-extern "C" int stk_wavelet_lift(int M, int J, int transpose, double *x, int ld, void *stream) {
+extern "C" int stk_wavelet_lift(int M, int J, int transpose, const double *src, double *x,
+                                int ld, void *stream) {
     if (J < 0 || J > 13) return fail(-1, "stk_wavelet_lift: J out of range [0, 13]");
     const int N = (1 << J) + 1;
     if (ld < N) return fail(-1, "stk_wavelet_lift: pitch smaller than 2^J + 1");
-    if (M == 0 || J == 0) return 0;
+    if (M == 0) return 0;
+    if (J == 0) {  // N = 2: the transform is the identity
+        if (src != x)
+            return check(cudaMemcpyAsync(x, src, sizeof(double) * (size_t)M * ld,
+                                         cudaMemcpyDeviceToDevice, as_stream(stream)),
+                         "stk_wavelet_lift: copy");
+        return 0;
+    }
     const int H = (1 << (J - 1)) + 1;
     size_t per_warp = sizeof(double) * ((size_t)N + 2 * H + (transpose ? N : 0));
     int wpb = (int)((200 * 1024) / per_warp);
@@ -113,12 +124,12 @@ extern "C" int stk_wavelet_lift(int M, int J, int transpose, double *x, int ld, 
         e = cudaFuncSetAttribute(k_wavelet_lift<true>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return check(e, "stk_wavelet_lift: smem attribute");
-        k_wavelet_lift<true><<<grid, wpb * 32, smem, as_stream(stream)>>>(M, J, x, ld);
+        k_wavelet_lift<true><<<grid, wpb * 32, smem, as_stream(stream)>>>(M, J, src, x, ld);
     } else {
         e = cudaFuncSetAttribute(k_wavelet_lift<false>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return check(e, "stk_wavelet_lift: smem attribute");
-        k_wavelet_lift<false><<<grid, wpb * 32, smem, as_stream(stream)>>>(M, J, x, ld);
+        k_wavelet_lift<false><<<grid, wpb * 32, smem, as_stream(stream)>>>(M, J, src, x, ld);
     }
     return check_launch("k_wavelet_lift");
 }

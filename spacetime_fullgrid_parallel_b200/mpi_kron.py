@@ -249,8 +249,13 @@ class MatKronIdentityMPI(LinearOperatorMPI):
         op = self.mat_time
         if isinstance(op, WaveletTransformOp):
             N = self.N
-            if op.interleaved:
-                res = sblock.clone()
+            if op.interleaved:  # out of place, one pass
+                res = torch.empty_like(sblock)
+                check(lib().stk_wavelet_lift(res.shape[0], op.J,
+                                             int(op.transposed), ptr(sblock),
+                                             ptr(res), res.shape[1],
+                                             stream()))
+                return res
             else:
                 if self._pos is None:
                     self._pos = torch.from_numpy(
@@ -262,7 +267,7 @@ class MatKronIdentityMPI(LinearOperatorMPI):
                     res[:, :N] = sblock[:, :N]
             check(lib().stk_wavelet_lift(res.shape[0], op.J,
                                          int(op.transposed), ptr(res),
-                                         res.shape[1], stream()))
+                                         ptr(res), res.shape[1], stream()))
             if not op.interleaved and op.transposed:
                 out = torch.zeros_like(res)
                 out[:, :N] = res[:, self._pos]

@@ -124,9 +124,10 @@ class WaveletTransformOp:
         """In-place on a device block (k, ld) holding the whole time axis of
         k columns; interleaved ordering."""
         assert self.interleaved
+        dst = x if out is None else out
         check(lib().stk_wavelet_lift(x.shape[0], self.J, int(self.transposed),
-                                     ptr(x), x.shape[1], stream()))
-        return x
+                                     ptr(x), ptr(dst), x.shape[1], stream()))
+        return dst
 
     def __matmul__(self, X):
         """Host arrays (N,) or (N, k), computed on the device."""
@@ -145,7 +146,7 @@ class WaveletTransformOp:
         blk[:, :self.N] = torch.from_numpy(np.ascontiguousarray(X2.T)).to(
             blk.device)
         check(lib().stk_wavelet_lift(k, self.J, int(self.transposed), ptr(blk),
-                                     ld, stream()))
+                                     ptr(blk), ld, stream()))
         Y = blk[:, :self.N].cpu().numpy().T
         if not self.interleaved and self.transposed:
             Y = Y[pos]
@@ -171,14 +172,11 @@ class WaveletTransformKronIdentityMPI(LinearOperatorMPI):
 
     def _matvec(self, vec_in, vec_out):
         if self.plan is None:
-            if vec_out is not vec_in:
-                vec_out._invalidate()
-                vec_out.data.copy_(vec_in.data)
             vec_out._invalidate()
             check(lib().stk_wavelet_lift(vec_out.M, self.J,
                                          int(self.transposed),
-                                         ptr(vec_out.data), vec_out.ld,
-                                         stream()))
+                                         ptr(vec_in.data), ptr(vec_out.data),
+                                         vec_out.ld, stream()))
             return vec_out
         assert vec_out is not vec_in
         t0 = self.plan.__dict__.get('time_communication', 0.0)

@@ -178,10 +178,10 @@ def test_pack_unpack_and_empty(cuda):
     check(L.stk_axpy(1.0, ptr(x), ptr(x), 0, None))
     check(L.stk_space_spmm(0, None, None, 1, None, None, None, None, ptr(x), 1.0, 0.0, None,
                            ptr(out), ld, None))
-    check(L.stk_wavelet_lift(0, 3, 0, ptr(x), 12, None))
+    check(L.stk_wavelet_lift(0, 3, 0, ptr(x), ptr(x), 12, None))
     # bad arguments come back as error codes with a message
     assert L.stk_axpy(1.0, ptr(x), ptr(x), 3, None) != 0
-    assert L.stk_wavelet_lift(4, 3, 0, ptr(x), 8, None) != 0  # pitch < 2^J + 1
+    assert L.stk_wavelet_lift(4, 3, 0, ptr(x), ptr(x), 8, None) != 0  # pitch < 2^J + 1
     assert len(L.stk_last_error()) > 0
 
 

@@ -40,6 +40,10 @@ def cuda():
     import torch
     if not torch.cuda.is_available():
         pytest.skip('no CUDA device')
-    from spacetime_fullgrid_parallel_b200 import _lib
+    from spacetime_fullgrid_parallel_b200 import _lib, build
+    try:  # rebuild if a source is newer than the library (no-op otherwise)
+        build.build_lib()
+    except Exception:
+        pass
     _lib.lib()  # fail loudly if the extension is missing on a GPU box
     return torch.device('cuda', 0)

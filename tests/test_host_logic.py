@@ -43,6 +43,11 @@ def test_abi_exports_every_declared_symbol():
         assert hasattr(lib, name), name
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     assert lib.stk_version() == 100
+    # the ctypes signatures carry as many arguments as the C declarations
+    for name, params in re.findall(r'\b(stk_[a-z0-9_]+)\s*\(([^)]*)\)', hdr):
+        params = params.strip()
+        n = 0 if params in ('', 'void') else params.count(',') + 1
+        assert n == len(_lib.SIGNATURES[name][1]), (name, n)
 
 
 def test_missing_library_fails_loudly(monkeypatch):

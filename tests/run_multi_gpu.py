@@ -66,6 +66,18 @@ def main():
         u = heq.W @ w
         ref = float(g[tag + '__norm_u'])
         assert abs(np.sqrt(u.dot(u)) - ref) < 1e-10 * ref, tag
+        # halo API (mpi_vector.py:140-203): neighbour slices and arbitrary
+        # remote slices arrive as device rows
+        prev, nxt = x.communicate_bdr()
+        if a > 0:
+            assert np.array_equal(prev.cpu().numpy(), X[a - 1]), (tag, 'bdr')
+        if b < heq.N:
+            assert np.array_equal(nxt.cpu().numpy(), X[b]), (tag, 'bdr')
+        want = [t for t in (0, heq.N // 2, heq.N - 1) if not a <= t < b]
+        got = x.communicate_dofs([(a, t) for t in want])
+        assert sorted(got) == want, (tag, 'dofs', sorted(got), want)
+        for t in want:
+            assert np.array_equal(got[t].cpu().numpy(), X[t]), (tag, 'dofs')
         # public permute round trip across ranks
         p = x.permute()
         assert np.array_equal(

@@ -264,3 +264,38 @@ def test_wavelet_transform_large(cuda):
         assert rel(y.X_loc, Wm @ X) < TOL
         z = wv.TransposedWaveletTransformKronIdentityMPI(d, J) @ y
         assert rel(z.X_loc, Wm.T @ (Wm @ X)) < TOL
+
+
+def test_serial_glue_and_shared_matrices(cuda):
+    """linop.py:6-15 (KronLinOp), :68-79 (CompositeLinOp), mpi_shared_mem.py
+    (device-resident matrices), wavelets.py:9-42 (WaveletTransformMat)."""
+    from spacetime_fullgrid_parallel_b200.linop import (CompositeLinOp,
+                                                        KronLinOp)
+    from spacetime_fullgrid_parallel_b200.mpi_kron import as_matrix
+    from spacetime_fullgrid_parallel_b200.mpi_shared_mem import (
+        shared_numpy_array, shared_sparse_matrix)
+    from spacetime_fullgrid_parallel_b200.wavelets import (WaveletTransformMat,
+                                                           WaveletTransformOp)
+    T = stiff5()
+    A = sp.random(7, 7, density=0.5, random_state=1, format='csr') + sp.identity(7)
+    B = sp.random(7, 7, density=0.5, random_state=2, format='csr')
+    x = rand((35, ), seed=3)
+    assert rel(KronLinOp(T, A.tocsr()) @ x,
+               np.kron(T.toarray(), A.toarray()) @ x) < TOL
+    dA = shared_sparse_matrix(A.tocsr())
+    assert dA.shape == (7, 7) and rel(dA @ np.eye(7), A.toarray()) < 1e-15
+    comp = CompositeLinOp([dA, B.tocsr(), dA])
+    assert rel(as_matrix(comp), (A @ B @ A).toarray()) < 1e-14
+    v = shared_numpy_array(np.arange(5.0))
+    assert v.is_cuda and v.cpu().tolist() == [0, 1, 2, 3, 4]
+    for J in (1, 3, 5):
+        assert rel(WaveletTransformMat(J).toarray(),
+                   WaveletTransformOp(J) @ np.eye(2**J + 1)) < 1e-13
+
+
+def test_halo_api_single_rank(cuda):
+    """communicate_bdr / communicate_dofs exist and are empty on one rank."""
+    d = _distr(5, 3)
+    v = _vec(d, rand((5, 3)))
+    assert v.communicate_bdr() == (None, None)
+    assert v.communicate_dofs([(0, 1), (4, 3)]) == {}

@@ -79,6 +79,31 @@ __device__ __forceinline__ double2 ldv2(const double *p) {
 __device__ __forceinline__ void stv2(double *p, double2 v) {
     *reinterpret_cast<double2 *>(p) = v;
 }
+// Four consecutive time values: one 256-bit global access (LDG.E.256 on
+// sm_100a; needs 32-byte alignment, which the pitch rule ld % 4 == 0 gives).
+struct __align__(32) double4v {
+    double x, y, z, w;
+};
+__device__ __forceinline__ double4v ldv4(const double *p) {
+    double4v v;
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w)
+                 : "l"(p)
+                 : "memory");
+    return v;
+}
+__device__ __forceinline__ void stv4(double *p, double4v v) {
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.x), "d"(v.y), "d"(v.z),
+                 "d"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ void fma4(double a, const double4v &x, double4v &s) {
+    s.x = fma(a, x.x, s.x);
+    s.y = fma(a, x.y, s.y);
+    s.z = fma(a, x.z, s.z);
+    s.w = fma(a, x.w, s.w);
+}
+
 __device__ __forceinline__ double2 ldg2(const double *p) {
     return __ldg(reinterpret_cast<const double2 *>(p));
 }

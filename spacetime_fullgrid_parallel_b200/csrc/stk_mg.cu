@@ -98,6 +98,57 @@ __global__ void __launch_bounds__(256, 8)
     }
 }
 
+// The same wavefront update with FOUR time values per thread (256-bit loads and
+// stores): twice the bytes in flight per warp for a latency-bound kernel.
+template <int K, bool FIRST>
+__global__ void __launch_bounds__(256)
+    k_gs_phase4(const int *__restrict__ rows, int nrows, const int *__restrict__ indptr,
+                const int *__restrict__ indices, const double *__restrict__ v0,
+                const double *__restrict__ v1, const double *__restrict__ d0,
+                const double *__restrict__ d1, const double *__restrict__ coef0,
+                const double *__restrict__ coef1, const double *__restrict__ f, double *u, int ld,
+                unsigned ld4) {
+    const unsigned total = (unsigned)nrows * ld4;
+    const unsigned stride = gridDim.x * 256u;
+    for (unsigned k = blockIdx.x * 256u + threadIdx.x; k < total; k += stride) {
+        unsigned r = k / ld4;
+        unsigned c = (k - r * ld4) * 4u;
+        int i = __ldg(rows + r);
+        int p0 = __ldg(indptr + i), p1 = __ldg(indptr + i + 1);
+        double4v s0 = {0.0, 0.0, 0.0, 0.0}, s1 = {0.0, 0.0, 0.0, 0.0};
+        for (int p = p0; p < p1; ++p) {
+            int j = __ldg(indices + p);
+            if (FIRST && j >= i) break;
+            double4v xv = ldv4(u + (size_t)j * ld + c);
+            fma4(__ldg(v0 + p), xv, s0);
+            if (K == 2) fma4(__ldg(v1 + p), xv, s1);
+        }
+        double4v diag;
+        if (K == 2) {
+            double4v c0 = ldv4(coef0 + c), c1 = ldv4(coef1 + c);
+            s0.x = fma(c0.x, s0.x, c1.x * s1.x);
+            s0.y = fma(c0.y, s0.y, c1.y * s1.y);
+            s0.z = fma(c0.z, s0.z, c1.z * s1.z);
+            s0.w = fma(c0.w, s0.w, c1.w * s1.w);
+            double e0 = __ldg(d0 + i), e1 = __ldg(d1 + i);
+            diag.x = fma(c0.x, e0, c1.x * e1);
+            diag.y = fma(c0.y, e0, c1.y * e1);
+            diag.z = fma(c0.z, e0, c1.z * e1);
+            diag.w = fma(c0.w, e0, c1.w * e1);
+        } else {
+            diag.x = diag.y = diag.z = diag.w = __ldg(d0 + i);
+        }
+        size_t o = (size_t)i * ld + c;
+        double4v fv = ldv4(f + o), uo = {0.0, 0.0, 0.0, 0.0};
+        if (!FIRST) uo = ldv4(u + o);
+        uo.x += (fv.x - s0.x) / diag.x;
+        uo.y += (fv.y - s0.y) / diag.y;
+        uo.z += (fv.z - s0.z) / diag.z;
+        uo.w += (fv.w - s0.w) / diag.w;
+        stv4(u + o, uo);
+    }
+}
+
 // u[i,t] = sum_j inv[g(t)][i,j] f[j,t]   (multigrid.py:161-170, exact solve).
 __global__ void __launch_bounds__(256)
     k_coarse_solve(int n0, const double *__restrict__ inv, const int *__restrict__ group,
@@ -168,12 +219,31 @@ static int smooth(const stk_mg *mg, int l, int nsweeps, bool backward, const dou
     k_gs_phase<KK, FF><<<resident_grid(k_gs_phase<KK, FF>, 256, (int64_t)nr * ld2), 256, 0, s>>>( \
         lv.sched + r0, nr, lv.indptr, lv.indices, lv.v0, lv.v1, lv.d0, lv.d1, c0, c1, f, u, ld,  \
         ld2)
+#define STK_GS4(KK, FF)                                                                       \
+    k_gs_phase4<KK, FF><<<resident_grid(k_gs_phase4<KK, FF>, 256, (int64_t)nr * (ld2 / 2)), 256,  \
+                          0, s>>>(lv.sched + r0, nr, lv.indptr, lv.indices, lv.v0, lv.v1, lv.d0, \
+                                  lv.d1, c0, c1, f, u, ld, ld2 / 2)
+            // STK_GS_VEC4: 0 = never, 1 = always, default = for K = 2 only (the
+            // per-slice-coefficient kernel gains ~5 % from 256-bit accesses, the
+            // single-matrix one loses ~1.5 %: measured, profiles/r1_experiments.md)
+            static const int vec4 = [] {
+                const char *e = getenv("STK_GS_VEC4");
+                return e ? atoi(e) : 2;
+            }();
+            if (vec4 == 1 || (vec4 == 2 && mg->K == 2)) {
+                if (mg->K == 2) {
+                    if (first) STK_GS4(2, true); else STK_GS4(2, false);
+                } else {
+                    if (first) STK_GS4(1, true); else STK_GS4(1, false);
+                }
+            } else
             if (mg->K == 2) {
                 if (first) STK_GS(2, true); else STK_GS(2, false);
             } else {
                 if (first) STK_GS(1, true); else STK_GS(1, false);
             }
 #undef STK_GS
+#undef STK_GS4
             STK_TRY(check_launch("k_gs_phase"));
         }
     }

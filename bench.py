@@ -364,7 +364,8 @@ def run_stk(args):
         except Exception:
             traffic = None
     roofline = {
-        'kernel': 'k_gs_phase<2> (one Gauss-Seidel wavefront, finest level)',
+        'kernel': ('k_gs_phase4<2,false> (one Gauss-Seidel wavefront, finest '
+                   'level, per-slice coefficients)'),
         'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
         'frac': achieved / peak, 'traffic': traffic, 'peak_source': which,
         'launch_ms': launch_ms, 'algorithmic_bytes_per_launch': bytes_per_launch

@@ -149,6 +149,21 @@ int stk_unpack_slices(double *x, int ld, int M, const int *tidx, int n,
 int stk_wavelet_lift(int M, int J, int transpose, const double *src,
                      double *x, int ld, void *stream);
 
+/* A chain of nlev sparse level steps along the time axis of the extended
+ * column [n_loc local slices | n_halo halo slices] of every space dof, in
+ * shared memory (the lifting form of the wavelet transform on a time slab of a
+ * P > 1 decomposition: wavelets.py:81-134 on the slices of mpi_vector.py:18-31
+ * plus the remote slices of mpi_kron.py:281-283).  Level l changes the rows
+ * trow[lev_ptr[l] .. lev_ptr[l+1]); row q is  sum_p tval[p] * col(tcol[p]),
+ * p in [tptr[q], tptr[q+1]), evaluated on the values before the level.
+ * xh: slice-major halo input (NULL = zeros); y: local result (pads zeroed);
+ * yh_out: slice-major (n_halo, M) halo part of the result or NULL. */
+int stk_time_chain(int M, int n_loc, int n_halo, int nlev, const int *lev_ptr,
+                   const int *trow, const int *tptr, const int *tcol,
+                   const double *tval, int R, int NNZ, const double *x,
+                   int ldx, const double *xh, double *y, int ldy,
+                   double *yh_out, void *stream);
+
 /* ---- multigrid V-cycle, batched over all time slices --------------------
  * multigrid.py:130-197 (MultiGrid), :100-127 (PETSc MatSOR sweeps).
  * A handle describes one Galerkin hierarchy (levels 0..nlevels-1, the last

@@ -51,6 +51,10 @@ SIGNATURES = {
     'stk_unpack_slices': (_int,
                           [_vp, _int, _int, _vp, _int, _vp, _dbl, _dbl, _vp]),
     'stk_wavelet_lift': (_int, [_int, _int, _int, _vp, _vp, _int, _vp]),
+    'stk_time_chain': (_int, [
+        _int, _int, _int, _int, _vp, _vp, _vp, _vp, _vp, _int, _int, _vp, _int,
+        _vp, _vp, _int, _vp, _vp
+    ]),
     'stk_mg_create': (_vp, [_int, _int, _int, _int]),
     'stk_mg_destroy': (None, [_vp]),
     'stk_mg_set_level': (_int, [

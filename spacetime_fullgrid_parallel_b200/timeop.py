@@ -153,7 +153,6 @@ class TimeOpPlan:
                                    ptr(vec_out.data), vec_out.ld, stream()))
         if not self.n_halo and not self.send_to:
             return
-        sends, recvs = {}, {}
         if self.n_halo:
             ldh = pitch(self.n_halo)
             part = torch.empty((M, ldh), dtype=torch.float64,
@@ -168,19 +167,102 @@ class TimeOpPlan:
             check(lib().stk_pack_slices(ptr(part), ldh, M,
                                         ptr(dev['halo_iota']), self.n_halo,
                                         ptr(packed), stream()))
+            self.scatter_add_halo(vec_out, packed)
+        else:
+            self.scatter_add_halo(vec_out, None)
+
+    def scatter_add_halo(self, vec_out, packed):
+        """The adjoint of `fetch`: `packed` (n_halo, M) holds this rank's
+        partial sums for slices owned by other ranks; they are sent to their
+        owners, and what the peers computed for this rank's slices is added
+        into vec_out."""
+        import torch
+        from ._lib import check, lib, ptr, stream
+        dev = self._device_arrays(vec_out.data.device)
+        M = vec_out.M
+        sends, recvs = {}, {}
+        if packed is not None:
             for p, (off, cnt) in self.recv_from.items():
                 sends[p] = packed[off:off + cnt]
         for p, idx in dev['send_idx'].items():
             recvs[p] = torch.empty((len(idx), M), dtype=torch.float64,
-                                   device=vec_in.data.device)
+                                   device=vec_out.data.device)
         t0 = _now()
-        vec_in.dofs_distr.comm.exchange(sends, recvs)
+        vec_out.dofs_distr.comm.exchange(sends, recvs)
         self.time_communication = getattr(self, 'time_communication',
                                           0.0) + _now() - t0
         for p, idx in dev['send_idx'].items():
             check(lib().stk_unpack_slices(ptr(vec_out.data), vec_out.ld, M,
                                           ptr(idx), len(idx), ptr(recvs[p]),
                                           1.0, 1.0, stream()))
+
+
+class LevelChain:
+    """A product of sparse level steps  G_L ... G_2 G_1  (x) I  restricted to
+    the extended index set [local slices | halo slices] of a TimeOpPlan.
+
+    The plan's halo set is the dependency closure of the local rows of the
+    whole product, so running the restricted steps one after the other on the
+    extended column reproduces the local rows exactly; entries of a step that
+    point outside the set belong to values no local row depends on and are
+    dropped.  Only the rows a step changes are stored.  Host logic (numpy);
+    `apply` runs stk_time_chain."""
+    def __init__(self, plan, steps):
+        self.plan = plan
+        n, nh = plan.n_loc, plan.n_halo
+        a = plan.dofs_distr.t_begin
+        E = np.concatenate([np.arange(a, a + n), plan.halo_cols]).astype(np.int64)
+        lev_ptr, trow, tptr, tcol, tval = [0], [], [0], [], []
+        eye = sp.identity(len(E), format='csr')
+        for G in steps:
+            G = sp.csr_matrix(G)[E][:, E].tocsr()
+            G.sort_indices()
+            changed = np.unique((G - eye).tocoo().row)
+            for r in changed:
+                lo, hi = G.indptr[r], G.indptr[r + 1]
+                trow.append(int(r))
+                tcol.extend(G.indices[lo:hi].tolist())
+                tval.extend(G.data[lo:hi].tolist())
+                tptr.append(len(tcol))
+            lev_ptr.append(len(trow))
+        self.lev_ptr = np.asarray(lev_ptr, dtype=np.int32)
+        self.trow = np.asarray(trow, dtype=np.int32)
+        self.tptr = np.asarray(tptr, dtype=np.int32)
+        self.tcol = np.asarray(tcol, dtype=np.int32)
+        self.tval = np.asarray(tval, dtype=np.float64)
+        self.nlev = len(steps)
+        self._dev = None
+
+    def apply_host(self, ext):
+        """The chain on an extended (n_loc + n_halo, k) host array (tests)."""
+        v = np.array(ext, dtype=np.float64, copy=True)
+        for lev in range(self.nlev):
+            q0, q1 = self.lev_ptr[lev], self.lev_ptr[lev + 1]
+            new = [sum(self.tval[p] * v[self.tcol[p]]
+                       for p in range(self.tptr[q], self.tptr[q + 1]))
+                   for q in range(q0, q1)]
+            for q, val in zip(range(q0, q1), new):
+                v[self.trow[q]] = val
+        return v
+
+    def apply(self, x_block, ldx, M, out_block, ldy, xh=None, yh_out=None):
+        import torch
+        from ._lib import check, lib, ptr, stream
+        dev = x_block.device
+        if self._dev is None:
+            # never hand an empty tensor's (null) pointer to the kernel
+            pad = lambda a: a if len(a) else np.zeros(1, dtype=a.dtype)
+            self._dev = tuple(
+                torch.from_numpy(pad(a)).to(dev)
+                for a in (self.lev_ptr, self.trow, self.tptr, self.tcol,
+                          self.tval))
+        lev_ptr, trow, tptr, tcol, tval = self._dev
+        check(lib().stk_time_chain(M, self.plan.n_loc, self.plan.n_halo,
+                                   self.nlev, ptr(lev_ptr), ptr(trow),
+                                   ptr(tptr), ptr(tcol), ptr(tval),
+                                   len(self.trow), len(self.tcol),
+                                   ptr(x_block), ldx, ptr(xh), ptr(out_block),
+                                   ldy, ptr(yh_out), stream()))
 
 
 class TimeOpPlan2:

@@ -17,7 +17,7 @@ import torch
 
 from ._lib import check, lib, ptr, stream
 from .mpi_kron import LinearOperatorMPI
-from .timeop import TimeOpPlan
+from .timeop import LevelChain, TimeOpPlan
 
 
 def wavelet_levels(J, interleaved=True):
@@ -166,9 +166,15 @@ class WaveletTransformKronIdentityMPI(LinearOperatorMPI):
         self.J = J
         self.op = WaveletTransformOp(J, interleaved=True)
         self.levels = self.op.levels
-        self.plan = None
+        self.plan = self.chain = None
         if dofs_distr.size > 1:
+            # exchange pattern from the product of all levels; arithmetic as a
+            # chain of lifting steps on [local | halo] columns
             self.plan = TimeOpPlan(dofs_distr, self.op.as_matrix())
+            steps = [_level_step(J, j) for j in range(1, J + 1)]
+            if self.transposed:
+                steps = [G.T.tocsr() for G in reversed(steps)]
+            self.chain = LevelChain(self.plan, steps)
 
     def _matvec(self, vec_in, vec_out):
         if self.plan is None:
@@ -180,11 +186,20 @@ class WaveletTransformKronIdentityMPI(LinearOperatorMPI):
             return vec_out
         assert vec_out is not vec_in
         t0 = self.plan.__dict__.get('time_communication', 0.0)
+        vec_out._invalidate()
+        pl = self.plan
         if self.transposed:
-            self.plan.apply_adjoint(vec_in, vec_out)
+            # local rows and the partial sums for remote slices in one pass,
+            # then the adjoint of the halo exchange
+            packed = torch.empty((pl.n_halo, vec_in.M), dtype=torch.float64,
+                                 device=vec_in.data.device) if pl.n_halo else None
+            self.chain.apply(vec_in.data, vec_in.ld, vec_in.M, vec_out.data,
+                             vec_out.ld, None, packed)
+            pl.scatter_add_halo(vec_out, packed)
         else:
-            vec_out._invalidate()
-            self.plan.apply(vec_in, vec_out.data)
+            halo = pl.fetch(vec_in) if pl.n_halo else None
+            self.chain.apply(vec_in.data, vec_in.ld, vec_in.M, vec_out.data,
+                             vec_out.ld, halo, None)
         self.time_communication += self.plan.__dict__.get(
             'time_communication', 0.0) - t0
         return vec_out

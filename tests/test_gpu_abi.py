@@ -200,3 +200,41 @@ def test_host_upload_download_entry_points(cuda):
         back = np.empty_like(X)
         check(L.stk_block_download_host(ptr(blk), ld, n_t, M, back.ctypes.data, ptr(tmp), None))
         assert np.array_equal(back, X)
+
+
+def test_time_chain_emulated_ranks(cuda):
+    """stk_time_chain on the slab of every rank of emulated decompositions
+    (halo slices supplied by hand): W rows and the adjoint with its halo
+    partial sums, against the sparse matrix."""
+    torch, check, L, ptr, pitch = _env()
+    from test_host_logic import FakeComm
+    from spacetime_fullgrid_parallel_b200.mpi_vector import DofDistributionMPI
+    from spacetime_fullgrid_parallel_b200.timeop import LevelChain, TimeOpPlan
+    from spacetime_fullgrid_parallel_b200.wavelets import (WaveletTransformOp,
+                                                           _level_step)
+    M = 77
+    for J, P in ((3, 2), (5, 4), (8, 8)):
+        N = 2**J + 1
+        W = WaveletTransformOp(J, interleaved=True).as_matrix()
+        X = rand((N, M), seed=J)
+        steps = [_level_step(J, j) for j in range(1, J + 1)]
+        WX = W @ X
+        for r in range(P):
+            d = DofDistributionMPI(FakeComm(r, P), N, M)
+            pl = TimeOpPlan(d, W)
+            a, b = d.t_begin, d.t_end
+            n, ld = b - a, pitch(b - a)
+            x = _block(torch, X[a:b], ld)
+            halo = torch.from_numpy(np.ascontiguousarray(X[pl.halo_cols])).cuda()
+            y = torch.full((M, ld), np.nan, dtype=torch.float64, device='cuda')
+            LevelChain(pl, steps).apply(x, ld, M, y, ld, halo if pl.n_halo else None, None)
+            got = y.cpu().numpy()
+            assert rel(got[:, :n].T, WX[a:b]) < 1e-13, (J, P, r)
+            assert np.all(got[:, n:] == 0.0)
+            ad = LevelChain(pl, [G.T.tocsr() for G in reversed(steps)])
+            yh = torch.full((max(pl.n_halo, 1), M), np.nan, dtype=torch.float64, device='cuda')
+            ad.apply(x, ld, M, y, ld, None, yh if pl.n_halo else None)
+            contrib = W[a:b].T @ X[a:b]
+            assert rel(y.cpu().numpy()[:, :n].T, contrib[a:b]) < 1e-13
+            if pl.n_halo:
+                assert rel(yh.cpu().numpy(), contrib[pl.halo_cols]) < 1e-13

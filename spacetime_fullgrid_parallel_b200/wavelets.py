@@ -74,6 +74,22 @@ def _level_step(J, j):
     return step
 
 
+def wavelet_dependency_pattern(J):
+    """Structural (0/1) pattern of the product of the J level steps: entry
+    (t, s) is set when input s can reach output t through the lifting steps.
+    It contains the pattern of W; the two differ where contributions cancel
+    exactly in the product (W[1, 2] = 0 although node 2 is an intermediate of
+    row 1), and a chain of level steps needs those intermediates too."""
+    S = sp.identity(2**J + 1, format='csr')
+    for j in range(1, J + 1):
+        F = _level_step(J, j).copy()
+        F.data = np.ones_like(F.data)
+        S = (F @ S).tocsr()
+        S.data = np.ones_like(S.data)
+    S.sort_indices()
+    return S
+
+
 def WaveletTransformMat(J):
     """The level-wise transform as an explicit sparse matrix (the debugging
     aid of wavelets.py:9-42)."""
@@ -168,13 +184,21 @@ class WaveletTransformKronIdentityMPI(LinearOperatorMPI):
         self.levels = self.op.levels
         self.plan = self.chain = None
         if dofs_distr.size > 1:
-            # exchange pattern from the product of all levels; arithmetic as a
-            # chain of lifting steps on [local | halo] columns
-            self.plan = TimeOpPlan(dofs_distr, self.op.as_matrix())
-            steps = [_level_step(J, j) for j in range(1, J + 1)]
-            if self.transposed:
-                steps = [G.T.tocsr() for G in reversed(steps)]
-            self.chain = LevelChain(self.plan, steps)
+            # exchange lists from the dependency pattern of the product of all
+            # levels (the closure of the local rows under the lifting steps);
+            # arithmetic as the chain of those steps on [local | halo] columns
+            import os
+            if os.environ.get('STK_WAVELET_CHAIN', '1') == '0':
+                # the fused-matrix form (one sparse time matrix with ~2J+1
+                # entries per row), kept as a cross-check of the chain
+                self.plan = TimeOpPlan(dofs_distr, self.op.as_matrix())
+            else:
+                self.plan = TimeOpPlan(dofs_distr,
+                                       wavelet_dependency_pattern(J))
+                steps = [_level_step(J, j) for j in range(1, J + 1)]
+                if self.transposed:
+                    steps = [G.T.tocsr() for G in reversed(steps)]
+                self.chain = LevelChain(self.plan, steps)
 
     def _matvec(self, vec_in, vec_out):
         if self.plan is None:
@@ -188,7 +212,12 @@ class WaveletTransformKronIdentityMPI(LinearOperatorMPI):
         t0 = self.plan.__dict__.get('time_communication', 0.0)
         vec_out._invalidate()
         pl = self.plan
-        if self.transposed:
+        if self.chain is None:
+            if self.transposed:
+                pl.apply_adjoint(vec_in, vec_out)
+            else:
+                pl.apply(vec_in, vec_out.data)
+        elif self.transposed:
             # local rows and the partial sums for remote slices in one pass,
             # then the adjoint of the halo exchange
             packed = torch.empty((pl.n_halo, vec_in.M), dtype=torch.float64,

@@ -210,18 +210,19 @@ def test_time_chain_emulated_ranks(cuda):
     from test_host_logic import FakeComm
     from spacetime_fullgrid_parallel_b200.mpi_vector import DofDistributionMPI
     from spacetime_fullgrid_parallel_b200.timeop import LevelChain, TimeOpPlan
-    from spacetime_fullgrid_parallel_b200.wavelets import (WaveletTransformOp,
-                                                           _level_step)
+    from spacetime_fullgrid_parallel_b200.wavelets import (
+        WaveletTransformOp, _level_step, wavelet_dependency_pattern)
     M = 77
-    for J, P in ((3, 2), (5, 4), (8, 8)):
+    for J, P in ((3, 2), (5, 4), (8, 8), (3, 8), (3, 9), (4, 16)):
         N = 2**J + 1
         W = WaveletTransformOp(J, interleaved=True).as_matrix()
+        pattern = wavelet_dependency_pattern(J)
         X = rand((N, M), seed=J)
         steps = [_level_step(J, j) for j in range(1, J + 1)]
         WX = W @ X
         for r in range(P):
             d = DofDistributionMPI(FakeComm(r, P), N, M)
-            pl = TimeOpPlan(d, W)
+            pl = TimeOpPlan(d, pattern)
             a, b = d.t_begin, d.t_end
             n, ld = b - a, pitch(b - a)
             x = _block(torch, X[a:b], ld)

@@ -18,6 +18,7 @@ from spacetime_fullgrid_parallel_b200.mpi_vector import (DofDistributionMPI,
 from spacetime_fullgrid_parallel_b200.timeop import LevelChain, TimeOpPlan
 from spacetime_fullgrid_parallel_b200.wavelets import (WaveletTransformOp,
                                                        _level_step,
+                                                       wavelet_dependency_pattern,
                                                        levelwise_positions,
                                                        wavelet_levels)
 
@@ -122,9 +123,10 @@ def test_timeop_plans():
 
 
 def test_wavelet_halo_is_small():
-    """W needs at most 2J-1 remote slices per rank."""
+    """W needs at most 2J-1 remote slices per rank at the
+    BASELINE decompositions (structural closure of the lifting steps)."""
     for J, P in ((8, 8), (10, 8), (6, 4)):
-        W = WaveletTransformOp(J, interleaved=True).as_matrix()
+        W = wavelet_dependency_pattern(J)
         for r in range(P):
             pl = TimeOpPlan(DofDistributionMPI(FakeComm(r, P), 2**J + 1, 1), W)
             assert pl.n_halo <= 2 * J - 1
@@ -189,30 +191,40 @@ def test_assembler():
 def test_level_chain_equals_wavelet_rows():
     """The lifting steps restricted to [local | halo] slices reproduce the
     local rows of W (and, transposed and reversed, of W^T with the partial
-    sums for the remote slices) for every rank of a decomposition."""
-    for J, P in ((3, 2), (4, 3), (6, 8), (8, 5)):
+    sums for the remote slices) for every rank of every decomposition, down to
+    one slice per rank.  The halo set must be the STRUCTURAL closure: W[1, 2]
+    is exactly zero although row 1 needs the intermediate value of node 2."""
+    W3 = WaveletTransformOp(3, interleaved=True).as_matrix()
+    assert W3[1, 2] == 0.0 and wavelet_dependency_pattern(3)[1, 2] == 1.0
+    for J in range(1, 8):
         N = 2**J + 1
         W = WaveletTransformOp(J, interleaved=True).as_matrix()
+        pattern = wavelet_dependency_pattern(J)
+        assert (abs(W) > 0).astype(int).multiply(pattern).sum() == W.nnz
         X = rand((N, 2), seed=J)
         steps = [_level_step(J, j) for j in range(1, J + 1)]
-        for r in range(P):
-            d = DofDistributionMPI(FakeComm(r, P), N, 1)
-            pl = TimeOpPlan(d, W)
-            a, b = d.t_begin, d.t_end
-            E = np.concatenate([np.arange(a, b), pl.halo_cols])
-            fw = LevelChain(pl, steps)
-            assert rel(fw.apply_host(X[E])[:b - a], (W @ X)[a:b]) < 1e-14
-            ad = LevelChain(pl, [G.T.tocsr() for G in reversed(steps)])
-            ext = np.zeros((len(E), 2))
-            ext[:b - a] = X[a:b]
-            contrib = W[a:b].T @ X[a:b]  # this rank's share of W^T X
-            assert rel(ad.apply_host(ext), contrib[E]) < 1e-14
-            rest = np.ones(N, dtype=bool)
-            rest[E] = False
-            assert not rest.any() or np.abs(contrib[rest]).max() == 0.0
+        for P in sorted({1, 2, 3, 5, 8, N // 2, N - 1, N} & set(range(1, N + 1))):
+            for r in range(P):
+                d = DofDistributionMPI(FakeComm(r, P), N, 1)
+                pl = TimeOpPlan(d, pattern)
+                assert pl.n_halo <= 2 * J
+                a, b = d.t_begin, d.t_end
+                E = np.concatenate([np.arange(a, b), pl.halo_cols])
+                fw = LevelChain(pl, steps)
+                assert np.abs(fw.apply_host(X[E])[:b - a] -
+                              (W @ X)[a:b]).max() < 1e-12, (J, P, r)
+                ad = LevelChain(pl, [G.T.tocsr() for G in reversed(steps)])
+                ext = np.zeros((len(E), 2))
+                ext[:b - a] = X[a:b]
+                contrib = W[a:b].T @ X[a:b]  # this rank's share of W^T X
+                assert np.abs(ad.apply_host(ext) - contrib[E]).max() < 1e-12
+                rest = np.ones(N, dtype=bool)
+                rest[E] = False
+                assert not rest.any() or np.abs(contrib[rest]).max() == 0.0
     # at the BASELINE size the chain does about a third of the multiply-adds
     J, P = 10, 8
-    W = WaveletTransformOp(J, interleaved=True).as_matrix()
-    pl = TimeOpPlan(DofDistributionMPI(FakeComm(3, P), 2**J + 1, 1), W)
+    pl = TimeOpPlan(DofDistributionMPI(FakeComm(3, P), 2**J + 1, 1),
+                    wavelet_dependency_pattern(J))
     fw = LevelChain(pl, [_level_step(J, j) for j in range(1, J + 1)])
-    assert 2.5 * len(fw.tcol) < pl.local.nnz
+    W = WaveletTransformOp(J, interleaved=True).as_matrix()
+    assert 2.5 * len(fw.tcol) < W[pl.dofs_distr.t_begin:pl.dofs_distr.t_end].nnz

@@ -23,7 +23,6 @@ import pickle
 import sys
 import zlib
 
-import numpy as np
 import psutil
 
 from .comm import Wtime, init_from_env, world
@@ -38,7 +37,7 @@ from .mpi_kron import (BlockDiagMPI, CompositeMPI, LinearOperatorMPI,
 from .timeop import TimeOpPlan, TimeOpPlan2
 from .mpi_shared_mem import shared_sparse_matrix
 from .mpi_vector import DofDistributionMPI, KronVectorMPI
-from .multigrid import MultiGrid, MultiGridFamily
+from .multigrid import MultiGridFamily
 from .wavelets import (TransposedWaveletTransformKronIdentityMPI,
                        WaveletTransformKronIdentityMPI, WaveletTransformOp)
 

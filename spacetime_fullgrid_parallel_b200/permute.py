@@ -9,7 +9,6 @@ from rank p at columns [t_p, t_p') of its (M_loc, ld(N)) "space-sharded block",
 in which the whole time axis of each owned space dof is contiguous: exactly
 what stk_time_apply wants.  `PermutePlan` is host logic (CPU-testable).
 """
-import numpy as np
 import torch
 
 from .mpi_vector import DofDistributionMPI, KronVectorMPI, pitch

@@ -228,3 +228,34 @@ def test_level_chain_equals_wavelet_rows():
     fw = LevelChain(pl, [_level_step(J, j) for j in range(1, J + 1)])
     W = WaveletTransformOp(J, interleaved=True).as_matrix()
     assert 2.5 * len(fw.tcol) < W[pl.dofs_distr.t_begin:pl.dofs_distr.t_end].nnz
+
+
+def test_wavefront_sweep_equals_sequential_sweep():
+    """Emulates what the GPU smoother does -- wavefront by wavefront, all rows
+    of a wavefront from the same old values, rows inside a wavefront in the
+    locality-sorted order -- and compares with the oracle's sequential
+    lexicographic sweeps (multigrid.py:89-97), forward and backward, for the
+    three numberings and for the 3-D cube."""
+    from oracle import cgs
+    from spacetime_fullgrid_parallel_b200.assembly import CubeProblem
+    from spacetime_fullgrid_parallel_b200.multigrid import gauss_seidel_schedule
+    cases = [SquareProblem(3, 1, order=o, seed=5) for o in ('class', 'lex', 'random')]
+    cases.append(CubeProblem(2, 1))
+    for prob in cases:
+        A = prob.Cinv_j[1].tocsr()
+        A.sort_indices()
+        n = A.shape[0]
+        rows, phase_ptr = gauss_seidel_schedule(A.indptr, A.indices)
+        diag = A.diagonal()
+        f, u0 = rand((n, ), seed=1), rand((n, ), seed=2)
+        for backward in (False, True):
+            ref = u0.copy()
+            cgs.gauss_seidel(A.indptr.astype(np.int32), A.indices.astype(np.int32),
+                             A.data, f, ref, 2, backward=backward)
+            u = u0.copy()
+            order = range(len(phase_ptr) - 1)
+            for _ in range(2):
+                for ph in (reversed(order) if backward else order):
+                    sel = rows[phase_ptr[ph]:phase_ptr[ph + 1]]
+                    u[sel] += (f[sel] - (A[sel] @ u)) / diag[sel]
+            assert rel(u, ref) < 1e-13

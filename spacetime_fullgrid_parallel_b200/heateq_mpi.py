@@ -16,16 +16,11 @@ slices in one batched V-cycle.
 Run:  python -m spacetime_fullgrid_parallel_b200.heateq_mpi --J_time 3 --J_space 6
       torchrun --nproc-per-node 2 -m spacetime_fullgrid_parallel_b200.heateq_mpi ...
 """
-import argparse
-import base64
 import os
-import pickle
-import sys
-import zlib
 
 import psutil
 
-from .comm import Wtime, init_from_env, world
+from .comm import Wtime, world
 from .linalg import PCG
 from .linop import CompositeLinOp
 import scipy.sparse as sp
@@ -199,76 +194,53 @@ class HeatEquationMPI:
 
 
 def main(argv=None):
-    parser = argparse.ArgumentParser(
-        description='Solve heatequation on B200s, parallel in time.')
-    parser.add_argument('--problem', default='square')
-    parser.add_argument('--J_time', type=int, default=7)
-    parser.add_argument('--J_space', type=int, default=7)
-    parser.add_argument('--smoothsteps', type=int, default=3)
-    parser.add_argument('--vcycles', type=int, default=2)
-    parser.add_argument('--wavelettransform', default='composite')
-    parser.add_argument('--alpha', type=float, default=0.3)
-    args = parser.parse_args(argv)
-
     import torch
-    comm = init_from_env()
-    rank, size = comm.Get_rank(), comm.Get_size()
-    data = {'rank': rank, 'size': size}
-    if size > 2**args.J_time + 1:
-        print('Too many MPI processors!')
-        sys.exit('1')
+    from . import _cli
+    args = _cli.parse('Solve heatequation on B200s, parallel in time.',
+                      'composite', argv=argv)
+    comm, data = _cli.start(args)
+    rank = data['rank']
     if rank == 0:
         print('\n\nCreating mesh with {} time refines and {} space refines.'.
               format(args.J_time, args.J_space))
-        print('MPI tasks: {} '.format(size))
+        print('MPI tasks: {} '.format(data['size']))
         print('Arguments: {}'.format(args))
-
-    heq = HeatEquationMPI(J_space=args.J_space, J_time=args.J_time,
-                          problem=args.problem, smoothsteps=args.smoothsteps,
-                          vcycles=args.vcycles, alpha=args.alpha,
-                          wavelettransform=args.wavelettransform, comm=comm)
+    heq = _cli.build(args, comm)
     if rank == 0:
-        data['args'] = vars(args)
-        data['N'], data['M'] = heq.N, heq.M
+        data.update(args=vars(args), N=heq.N, M=heq.M)
         print('N = {}. M = {}.'.format(heq.N, heq.M))
         print('Constructed bilinear forms in {} s.'.format(heq.setup_time))
-        print('Memory after ngsolve: {}mb.'.format(heq.mem_after_ngsolve))
-        print('Memory after shared mat: {}mb.'.format(
-            heq.mem_after_shared_matrices))
-        print('Memory after precond: {}mb.'.format(heq.mem_after_precond))
-        print('Memory after construction: {}mb.'.format(mem()))
+        for label, value in (('ngsolve', heq.mem_after_ngsolve),
+                             ('shared mat', heq.mem_after_shared_matrices),
+                             ('precond', heq.mem_after_precond),
+                             ('construction', mem())):
+            print('Memory after {}: {}mb.'.format(label, value))
     data['mem_after_construction'] = mem()
 
-    def cb(w, residual, k):
+    def progress(w, residual, k):
         if rank == 0:
             print('.', end='', flush=True)
 
+    # everyone starts the solve together (heateq_mpi.py:280-288); the device
+    # is drained on both sides so that solve_time is the time to solution
     torch.cuda.synchronize()
     comm.Barrier()
-    solve_time = Wtime()
-    u, iters = PCG(heq.WT_S_W, heq.P, heq.rhs, callback=cb)
+    t0 = Wtime()
+    u, iters = PCG(heq.WT_S_W, heq.P, heq.rhs, callback=progress)
     torch.cuda.synchronize()
     comm.Barrier()
-    data['solve_time'] = Wtime() - solve_time
-    data['mem_after_solve'] = mem()
-    data['iters'] = iters
+    data.update(solve_time=Wtime() - t0, mem_after_solve=mem(), iters=iters)
     for name in ('W', 'S', 'WT', 'P', 'WT_S_W'):
         op = getattr(heq, name)
-        data[name] = {
-            'time_applies': op.time_applies,
-            'time_communication': op.time_communication,
-            'num_applies': op.num_applies
-        }
+        data[name] = {key: getattr(op, key) for key in
+                      ('time_applies', 'time_communication', 'num_applies')}
     if rank == 0:
         print('')
         print('Completed in {} PCG steps.'.format(iters))
         print('Total solve time: {}s.'.format(data['solve_time']))
         heq.print_time_per_apply()
         print('Memory after solve: {}mb.'.format(mem()))
-    data = comm.gather(data, root=0)
-    if rank == 0:
-        print('\ndata: {}'.format(
-            str(base64.b64encode(zlib.compress(pickle.dumps(data))), 'ascii')))
+    _cli.finish(comm, data)
     return u, iters
 
 

@@ -1,0 +1,88 @@
+"""CPU: the drivers' command line, banner and `data:` blob (heateq_mpi.py:205-312)
+with the device objects replaced by numpy stand-ins."""
+import base64
+import pickle
+import zlib
+
+import numpy as np
+import scipy.sparse as sp
+
+from spacetime_fullgrid_parallel_b200 import _cli, heateq_mpi
+
+
+class _Op:
+    """Host operator with the counters the driver serialises."""
+    def __init__(self, mat):
+        self.mat = mat
+        self.num_applies, self.time_applies, self.time_communication = 0, 0.0, 0.0
+
+    def __matmul__(self, x):
+        self.num_applies += 1
+        self.time_applies += 1e-3
+        return self.mat @ x
+
+    def time_per_apply(self):
+        return (self.time_applies / max(self.num_applies, 1), 0.0)
+
+
+class _FakeHeatEq:
+    N, M = 5, 7
+    setup_time = 0.0
+    mem_after_ngsolve = mem_after_shared_matrices = mem_after_precond = 1.0
+
+    def __init__(self):
+        n = self.N * self.M
+        A = sp.diags([np.full(n - 1, -1.0), np.full(n, 2.5), np.full(n - 1, -1.0)],
+                     [-1, 0, 1], format='csr')
+        self.W = self.WT = _Op(sp.identity(n, format='csr'))
+        self.S = self.WT_S_W = _Op(A)
+        self.P = _Op(sp.identity(n, format='csr'))
+        self.rhs = np.ones(n)
+
+    print_time_per_apply = heateq_mpi.HeatEquationMPI.print_time_per_apply
+
+
+def test_flags_match_the_reference_defaults():
+    a = _cli.parse('x', 'composite', argv=[])
+    assert vars(a) == dict(problem='square', J_time=7, J_space=7, smoothsteps=3, vcycles=2,
+                           alpha=0.3, wavelettransform='composite')  # heateq_mpi.py:208-234
+    t = _cli.parse('x', 'original', extra=(('--iters', int, 10, ''), ), argv=['--iters', '3'])
+    assert t.wavelettransform == 'original' and t.iters == 3  # heateq_mpi_timing.py:35-42
+
+
+def test_driver_main_report_and_blob(monkeypatch, capsys):
+    import torch
+    monkeypatch.setattr(torch.cuda, 'synchronize', lambda *a, **k: None)
+    monkeypatch.setattr(_cli, 'build', lambda args, comm: _FakeHeatEq())
+    u, iters = heateq_mpi.main(['--J_time', '2', '--J_space', '1'])
+    out = capsys.readouterr().out
+    assert 'Completed in {} PCG steps.'.format(iters) in out and 'N = 5. M = 7.' in out
+    blob = [l for l in out.splitlines() if l.startswith('data: ')][0][6:]
+    records = pickle.loads(zlib.decompress(base64.b64decode(blob)))
+    assert len(records) == 1
+    rec = records[0]
+    assert rec['rank'] == 0 and rec['size'] == 1 and rec['iters'] == iters
+    assert rec['args']['J_time'] == 2 and rec['N'] == 5 and rec['M'] == 7
+    for name in ('W', 'S', 'WT', 'P', 'WT_S_W'):  # heateq_mpi.py:293-300
+        assert set(rec[name]) == {'time_applies', 'time_communication', 'num_applies'}
+    assert rec['WT_S_W']['num_applies'] == iters  # zero start: no initial apply
+    assert {'solve_time', 'mem_after_solve', 'mem_after_construction'} <= set(rec)
+
+
+def test_too_many_ranks_guard(monkeypatch):
+    class Big:
+        def Get_size(self):
+            return 6
+
+        def Get_rank(self):
+            return 0
+
+    from spacetime_fullgrid_parallel_b200 import comm as stk_comm
+    monkeypatch.setattr(stk_comm, 'init_from_env', lambda: Big())
+    args = _cli.parse('x', 'composite', argv=['--J_time', '2'])  # N = 5 < 6 ranks
+    try:
+        _cli.start(args)
+    except SystemExit as e:
+        assert str(e.code) == '1'  # heateq_mpi.py:241-243
+    else:
+        raise AssertionError('expected SystemExit')

@@ -86,3 +86,45 @@ def test_too_many_ranks_guard(monkeypatch):
         assert str(e.code) == '1'  # heateq_mpi.py:241-243
     else:
         raise AssertionError('expected SystemExit')
+
+
+def test_timing_driver_report_and_blob(monkeypatch, capsys):
+    """heateq_mpi_timing.py:81-128: per-operator lists in the blob."""
+    import torch
+    from spacetime_fullgrid_parallel_b200 import heateq_mpi_timing as timing
+
+    class FakeVec:
+        def __init__(self, dofs_distr):
+            self.n_loc, self.M = 5, 7
+            self._x = np.zeros((5, 7))
+
+        @property
+        def X_loc(self):
+            return self._x
+
+        def _invalidate(self):
+            pass
+
+    class VecOp(_Op):
+        def __matmul__(self, v):
+            self.num_applies += 1
+            self.time_applies += 2e-3
+            return v
+
+    fake = _FakeHeatEq()
+    fake.dofs_distr = None
+    fake.W, fake.WT, fake.S, fake.P = (VecOp(None) for _ in range(4))
+    monkeypatch.setattr(timing, 'KronVectorMPI', FakeVec)
+    monkeypatch.setattr(_cli, 'build', lambda args, comm: fake)
+    monkeypatch.setattr(torch.cuda, 'max_memory_reserved', lambda *a: 0)
+    records = timing.main(['--J_time', '2', '--J_space', '1', '--iters', '3'])
+    out = capsys.readouterr().out
+    assert 'Completed 3 iters steps.' in out and out.count('median') == 4
+    rec = records[0]
+    assert rec['args']['wavelettransform'] == 'original' and rec['args']['iters'] == 3
+    for name in ('W', 'S', 'WT', 'P'):  # heateq_mpi_timing.py:104-111
+        assert {'time_applies', 'time_communication', 'time_applies_iter',
+                'time_communication_iter', 'num_applies', 'time_total'} <= set(rec[name])
+        assert rec[name]['num_applies'] == 3 and len(rec[name]['time_applies_iter']) == 3
+    from spacetime_fullgrid_parallel_b200.mpi_kron import LinearOperatorMPI
+    assert LinearOperatorMPI.sync_timing is False  # restored

@@ -259,3 +259,40 @@ def test_wavefront_sweep_equals_sequential_sweep():
                     sel = rows[phase_ptr[ph]:phase_ptr[ph + 1]]
                     u[sel] += (f[sel] - (A[sel] @ u)) / diag[sel]
             assert rel(u, ref) < 1e-13
+
+
+def test_chained_wavelet_all_ranks_with_exchange():
+    """W and W^T over ALL ranks of a decomposition through the chain, with the
+    halo exchange and its adjoint emulated exactly as `fetch` /
+    `scatter_add_halo` pair the send and receive lists (what the 8-GPU run
+    exercises), down to one slice per rank."""
+    for J, P in ((3, 8), (3, 9), (2, 4), (4, 16), (5, 3), (6, 8)):
+        N = 2**J + 1
+        W = WaveletTransformOp(J, interleaved=True).as_matrix()
+        pattern = wavelet_dependency_pattern(J)
+        steps = [_level_step(J, j) for j in range(1, J + 1)]
+        X = rand((N, 3), seed=10 * J + P)
+        plans = [TimeOpPlan(DofDistributionMPI(FakeComm(r, P), N, 3), pattern)
+                 for r in range(P)]
+        bounds = plans[0].dofs_distr.dof_distribution
+        fw = [LevelChain(pl, steps) for pl in plans]
+        ad = [LevelChain(pl, [G.T.tocsr() for G in reversed(steps)]) for pl in plans]
+        out_w = np.zeros_like(X)
+        out_wt = np.zeros_like(X)
+        packed = []
+        for r, pl in enumerate(plans):
+            a, b = bounds[r]
+            halo = np.zeros((pl.n_halo, 3))
+            for p, (off, cnt) in pl.recv_from.items():  # fetch: p packs send_to[r]
+                halo[off:off + cnt] = X[bounds[p][0] + plans[p].send_to[r]]
+            out_w[a:b] = fw[r].apply_host(np.concatenate([X[a:b], halo]))[:b - a]
+            ext = np.zeros((b - a + pl.n_halo, 3))
+            ext[:b - a] = X[a:b]
+            y = ad[r].apply_host(ext)
+            out_wt[a:b] += y[:b - a]
+            packed.append(y[b - a:])
+        for r, pl in enumerate(plans):  # scatter_add_halo: r sends packed[off:off+cnt] to p
+            for p, (off, cnt) in pl.recv_from.items():
+                out_wt[bounds[p][0] + plans[p].send_to[r]] += packed[r][off:off + cnt]
+        assert np.abs(out_w - W @ X).max() < 1e-12, (J, P)
+        assert np.abs(out_wt - W.T @ X).max() < 1e-12, (J, P)

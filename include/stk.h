@@ -211,6 +211,47 @@ int stk_mg_smooth(stk_mg *mg, int level, int nsweeps, int backward,
  * rows one by one). */
 int stk_gs_wavefronts(int n, const int *indptr, const int *indices, int *wave);
 
+/* ---- fused Gauss-Seidel smoother -----------------------------------------
+ * `nsweeps` lexicographic sweeps of one level (multigrid.py:89-97, MatSOR
+ * :113-127) in one pass over HBM.  A program (built on the host by
+ * gs_program.compile_program; all array arguments are DEVICE pointers the
+ * caller keeps alive, except none) lists, per spatial item and macro-step, the
+ * shared-memory window loads and the row updates that may run concurrently;
+ * see csrc/stk_gsfused.cu.  item_step / item_pass: nitems + 1 ints;
+ * step_info: (end pass, end load) int pairs per macro-step; rec: npasses x
+ * ngrp records of recw uint32 (row, prefetch hint, kind or CSR offset, window
+ * slot | nnz << 16, then the uint16 window slots of the row's entries);
+ * ld: (row, window slot) int pairs; ngrp = row updates a CTA runs side by
+ * side (128 or 256: 512 or 1024 threads, 4 lanes per row). */
+typedef struct stk_gs_prog stk_gs_prog;
+stk_gs_prog *stk_gs_prog_create(int nitems, int nslots, int maxnnz, int generic,
+                                int recw, int ngrp, const int *item_step,
+                                const int *item_pass, const void *step_info,
+                                const void *rec, const void *ld);
+void stk_gs_prog_destroy(stk_gs_prog *prog);
+/* u_out <- the program's sweeps applied to u_in (NULL: zero initial guess) with
+ * right-hand side f; u_in must not alias u_out.  T = time values per CTA (8).  Matrix values: the kind table ktab[nkinds][K*maxnnz + 2] (per kind:
+ * K = 1: values, diagonal, spare; K = 2: (v0, v1) pairs, then the two
+ * diagonals) for programs compiled with row kinds, else the level's CSR value
+ * arrays v0/v1 and diagonals d0/d1.  coef0/coef1: per-slice coefficients
+ * (K = 2). */
+int stk_gs_fused(const stk_gs_prog *prog, int K, int T, const double *ktab,
+                 int nkinds, const double *v0, const double *v1,
+                 const double *d0, const double *d1, const double *coef0,
+                 const double *coef1, const double *f, const double *u_in,
+                 double *u_out, int ld, void *stream);
+/* Attach the fused smoother programs (nu forward / nu backward sweeps) and the
+ * kind table of this handle's values to a level of a multigrid hierarchy;
+ * stk_mg_apply then runs each smoothing phase of that level as one launch
+ * (and needs one more block of workspace per fused level, see
+ * stk_mg_workspace).  Call before the first stk_mg_apply. */
+int stk_mg_set_fused(stk_mg *mg, int level, const stk_gs_prog *fwd,
+                     const stk_gs_prog *bwd, const double *ktab, int nkinds,
+                     int T);
+/* HOST helper (host pointers): interval colouring of window lifetimes
+ * [start[q], end[q]] (macro-steps); slot[q] out; returns the slots used. */
+int stk_gs_alloc_slots(int n, const int *start, const int *end, int *slot);
+
 #ifdef __cplusplus
 }
 #endif

@@ -68,6 +68,16 @@ SIGNATURES = {
         _vp, _int, _int, _int, _vp, _vp, _vp, _vp, _int, _vp
     ]),
     'stk_gs_wavefronts': (_int, [_int, _vp, _vp, _vp]),
+    'stk_gs_alloc_slots': (_int, [_int, _vp, _vp, _vp]),
+    'stk_gs_prog_create': (_vp, [
+        _int, _int, _int, _int, _int, _int, _vp, _vp, _vp, _vp, _vp
+    ]),
+    'stk_gs_prog_destroy': (None, [_vp]),
+    'stk_mg_set_fused': (_int, [_vp, _int, _vp, _vp, _vp, _int, _int]),
+    'stk_gs_fused': (_int, [
+        _vp, _int, _int, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+        _vp, _int, _vp
+    ]),
 }
 
 _lib = None

@@ -11,7 +11,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libstk.so')
-SOURCES = ['stk_blas1.cu', 'stk_kron.cu', 'stk_wavelet.cu', 'stk_mg.cu']
+SOURCES = ['stk_blas1.cu', 'stk_kron.cu', 'stk_wavelet.cu', 'stk_mg.cu',
+           'stk_gsfused.cu']
 NVCC_FLAGS = [
     '-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a',
     '-lineinfo', '-Xcompiler', '-fPIC', '-shared', '--fmad=true',

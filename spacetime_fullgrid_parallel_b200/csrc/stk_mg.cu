@@ -23,6 +23,13 @@ int launch_space_spmm(int nrows, const int *indptr, const int *indices, int K,
                       const double *vals0, const double *vals1, const double *coef0,
                       const double *coef1, const double *x, double alpha, double beta,
                       const double *z, double *y, int ld, cudaStream_t s);
+}  // namespace stk
+struct stk_gs_prog;
+namespace stk {
+int gs_fused_run(const stk_gs_prog *pg, int K, int T, const double *ktab, int nkinds,
+                 const double *v0, const double *v1, const double *d0, const double *d1,
+                 const double *coef0, const double *coef1, const double *f, const double *uin,
+                 double *uout, int ld, cudaStream_t s);
 
 struct Level {
     int n = 0;
@@ -35,6 +42,11 @@ struct Level {
     const double *p_vals = nullptr;
     const int *r_indptr = nullptr, *r_indices = nullptr;
     const double *r_vals = nullptr;
+    // fused smoother (stk_gsfused.cu): nu forward / nu backward sweeps as one
+    // launch each, out of place; null = per-wavefront launches
+    const stk_gs_prog *fused_fwd = nullptr, *fused_bwd = nullptr;
+    const double *ktab = nullptr;
+    int nkinds = 0, fused_T = 8;
 };
 
 // u_i += (f_i - A_i . u) / a_ii for the rows of one wavefront
@@ -252,8 +264,17 @@ static int smooth(const stk_mg *mg, int l, int nsweeps, bool backward, const dou
 
 struct Workspace {
     std::vector<double *> u, f;  // per level below the finest
+    std::vector<double *> alt;   // per fused level: output of the pre-smoother
     double *res;                 // residual of the current level
 };
+
+static int smooth_fused(const stk_mg *mg, int l, bool backward, const double *c0, const double *c1,
+                        const double *f, const double *uin, double *uout, int ld,
+                        cudaStream_t s) {
+    const Level &lv = mg->L[l];
+    return gs_fused_run(backward ? lv.fused_bwd : lv.fused_fwd, mg->K, lv.fused_T, lv.ktab,
+                        lv.nkinds, lv.v0, lv.v1, lv.d0, lv.d1, c0, c1, f, uin, uout, ld, s);
+}
 
 static int coarse_solve(const stk_mg *mg, const double *inv, const int *group, const double *f,
                         double *u, int ld, cudaStream_t s) {
@@ -270,22 +291,34 @@ static int cycle(const stk_mg *mg, int l, const double *c0, const double *c1, co
     if (l == 0) return coarse_solve(mg, inv, group, f, u, ld, s);
     const Level &lv = mg->L[l];
     const Level &lc = mg->L[l - 1];
-    if (zero_guess && mg->nu == 0)
-        STK_TRY(check(cudaMemsetAsync(u, 0, sizeof(double) * (size_t)lv.n * ld, s),
-                      "stk_mg: memset"));
-    STK_TRY(smooth(mg, l, mg->nu, false, c0, c1, f, u, ld, s, zero_guess));
+    const bool fused = lv.fused_fwd && lv.fused_bwd && mg->nu > 0 && ws.alt[l];
+    // `cur` holds the iterate between the two smoothers: the fused smoother
+    // works out of place (items re-read rows of their neighbours' halo), so
+    // the pre-smoother writes to the level's alternate block and the
+    // post-smoother brings the result back to u.
+    double *cur = u;
+    if (fused) {
+        cur = ws.alt[l];
+        STK_TRY(smooth_fused(mg, l, false, c0, c1, f, zero_guess ? nullptr : u, cur, ld, s));
+    } else {
+        if (zero_guess && mg->nu == 0)
+            STK_TRY(check(cudaMemsetAsync(u, 0, sizeof(double) * (size_t)lv.n * ld, s),
+                          "stk_mg: memset"));
+        STK_TRY(smooth(mg, l, mg->nu, false, c0, c1, f, u, ld, s, zero_guess));
+    }
     // res = A u - f, f_c = R res (multigrid.py:174).  A fused kernel that
     // recomputes the fine residuals per coarse row was measured 2.6x slower
     // (6 block passes of DRAM reads instead of ~3): the residual block costs
     // less than the lost locality.
-    STK_TRY(launch_space_spmm(lv.n, lv.indptr, lv.indices, mg->K, lv.v0, lv.v1, c0, c1, u, 1.0,
+    STK_TRY(launch_space_spmm(lv.n, lv.indptr, lv.indices, mg->K, lv.v0, lv.v1, c0, c1, cur, 1.0,
                               -1.0, f, ws.res, ld, s));
     STK_TRY(launch_space_spmm(lc.n, lv.r_indptr, lv.r_indices, 1, lv.r_vals, nullptr, nullptr,
                               nullptr, ws.res, 1.0, 0.0, nullptr, ws.f[l - 1], ld, s));
     STK_TRY(cycle(mg, l - 1, c0, c1, inv, group, ws.f[l - 1], ws.u[l - 1], ld, ws, s, true));
     // u -= P u_c
     STK_TRY(launch_space_spmm(lv.n, lv.p_indptr, lv.p_indices, 1, lv.p_vals, nullptr, nullptr,
-                              nullptr, ws.u[l - 1], -1.0, 1.0, u, u, ld, s));
+                              nullptr, ws.u[l - 1], -1.0, 1.0, cur, cur, ld, s));
+    if (fused) return smooth_fused(mg, l, true, c0, c1, f, cur, u, ld, s);
     return smooth(mg, l, mg->nu, true, c0, c1, f, u, ld, s);
 }
 
@@ -347,7 +380,25 @@ int64_t stk_mg_workspace(const stk_mg *mg, int ld) {
     int64_t rows = 0;
     for (int l = 0; l + 1 < mg->nlevels; ++l) rows += 2 * (int64_t)mg->L[l].n;
     rows += mg->L[mg->nlevels - 1].n;
+    for (int l = 1; l < mg->nlevels; ++l)
+        if (mg->L[l].fused_fwd && mg->L[l].fused_bwd) rows += mg->L[l].n;
     return rows * ld;
+}
+
+int stk_mg_set_fused(stk_mg *mg, int level, const stk_gs_prog *fwd, const stk_gs_prog *bwd,
+                     const double *ktab, int nkinds, int T) {
+    if (!mg || level < 1 || level >= mg->nlevels) return fail(-1, "stk_mg_set_fused: bad level");
+    if (T != 8) return fail(-1, "stk_mg_set_fused: T must be 8");
+    Level &lv = mg->L[level];
+    lv.fused_fwd = fwd;
+    lv.fused_bwd = bwd;
+    lv.ktab = ktab;
+    lv.nkinds = nkinds;
+    lv.fused_T = T;
+    for (auto &kv : mg->graphs)  // captured sequences are stale now
+        if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    mg->graphs.clear();
+    return 0;
 }
 
 int stk_mg_apply(stk_mg *mg, const double *coef0, const double *coef1, const double *coarse_inv,
@@ -370,6 +421,13 @@ int stk_mg_apply(stk_mg *mg, const double *coef0, const double *coef1, const dou
         q += (size_t)mg->L[l].n * ld;
     }
     ws.res = q;
+    q += (size_t)mg->L[top].n * ld;
+    ws.alt.assign(mg->nlevels, nullptr);
+    for (int l = 1; l <= top; ++l)
+        if (mg->L[l].fused_fwd && mg->L[l].fused_bwd) {
+            ws.alt[l] = q;
+            q += (size_t)mg->L[l].n * ld;
+        }
     auto run = [&](cudaStream_t st) -> int {
         if (mg->vcycles == 0)
             STK_TRY(check(cudaMemsetAsync(x, 0, sizeof(double) * (size_t)mg->L[top].n * ld, st),

@@ -146,8 +146,10 @@ class HeatEquationMPI:
                 "precond=%r: the device path implements 'multigrid' only" %
                 precond)
         hierarchy = prob.hierarchy
+        from .mpi_vector import pitch
         self.family = MultiGridFamily([prob.M_x, prob.A_x], hierarchy,
-                                      smoothsteps=smoothsteps, vcycles=vcycles)
+                                      smoothsteps=smoothsteps, vcycles=vcycles,
+                                      ld_hint=pitch(self.dofs_distr.n_loc))
         self.Kinv_x = self.family.member((0.0, 1.0))
         self.C_j = [
             self.family.member((2.0**j, alpha)) for j in range(J_time + 1)

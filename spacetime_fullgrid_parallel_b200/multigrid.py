@@ -14,16 +14,138 @@ and all C_j = MG(2^j M_x + alpha A_x), heateq_mpi.py:143-153) from ONE
 device-resident hierarchy with per-slice coefficients.
 """
 import ctypes
+import os
 
 import numpy as np
 import scipy.sparse as sp
 import torch
 
+from . import gs_program
 from ._lib import check, lib, ptr, stream
 from .linop import host_apply
 from .mpi_vector import _device
 
 MAX_COARSE = 1024
+# fused smoother (gs_program.py / csrc/stk_gsfused.cu): time values per CTA,
+# shared memory the window + kind tables may take, smallest level worth it
+FUSED_T = int(os.environ.get('STK_GS_T', '8'))
+FUSED_SMEM = 224 * 1024
+FUSED_MIN_ROWS = int(os.environ.get('STK_GS_FUSED_MIN_ROWS', '256'))
+FUSED_NGRP = int(os.environ.get('STK_GS_NGRP', '128'))  # 512 threads / 4 lanes
+
+
+def fused_enabled():
+    return os.environ.get('STK_GS_FUSED', '1') != '0'
+
+
+def _dev_bytes(a, device, keep):
+    """Upload a NumPy array of any integer width as raw bytes."""
+    a = np.ascontiguousarray(a)
+    t = torch.from_numpy(a.view(np.uint8).reshape(-1)).to(device)
+    keep.append(t)
+    return t
+
+
+class FusedLevel:
+    """Device-resident programs of one level: nu forward and nu backward
+    sweeps, plus the row kinds that index a handle's value table."""
+    def __init__(self, indptr, indices, wave, nsweeps, value_arrays,
+                 diag_arrays, device, chunks=33, sms=148, T=None,
+                 generic=False, capacity=None, ngrp=None):
+        self.ok = False
+        self.handles = []
+        self._keep = []
+        self.T = T = FUSED_T if T is None else T
+        self.maxnnz = int(np.diff(indptr).max())
+        # the kernel's branch-free row product holds <= 8 entries per row
+        kinds = None if generic or self.maxnnz > 8 else gs_program.row_kinds(
+            indptr, value_arrays, diag_arrays)
+        if kinds is None:
+            self.kind_of_row, self.rep = None, None
+            self.nkinds, tab_bytes = 0, 0
+        else:
+            self.kind_of_row, self.rep = kinds
+            self.nkinds = len(self.rep)
+            # the widest table any handle on this pattern may need (K = 2)
+            tab_bytes = 8 * self.nkinds * (2 * self.maxnnz + 4 + T + 2) + 16
+        ngrp = FUSED_NGRP if ngrp is None else ngrp
+        if capacity is None:
+            # what the window may take: shared memory minus the value tables
+            # and the record / f rings (csrc/stk_gsfused.cu)
+            rings = gs_program.PREFETCH * ngrp * (32 + 8 * T)
+            capacity = min(65535, (FUSED_SMEM - tab_bytes - rings) // (8 * T))
+        n = len(indptr) - 1
+        emb = gs_program.graph_embedding(
+            np.ascontiguousarray(indptr, dtype=np.int32),
+            np.ascontiguousarray(indices, dtype=np.int32), n)
+        if emb is None:
+            return
+        progs = []
+        for backward in (False, True):
+            pg = gs_program.compile_program(
+                indptr, indices, wave, nsweeps, backward, capacity,
+                embedding=emb, kind_of_row=self.kind_of_row,
+                chunks=chunks, sms=sms,
+                ngrp=ngrp)
+            if pg is None:
+                return
+            progs.append(pg)
+        self.programs = progs
+        for pg in progs:
+            d = [_dev_bytes(x, device, self._keep)
+                 for x in (pg.item_step, pg.item_pass, pg.step_info, pg.op,
+                           pg.ld)]
+            h = ctypes.c_void_p(lib().stk_gs_prog_create(
+                pg.nitems, pg.nslots, pg.maxnnz, int(pg.generic), pg.recw,
+                pg.ngrp, *[ptr(t) for t in d]))
+            assert h.value, 'stk_gs_prog_create failed'
+            self.handles.append(h)
+        self.indptr = np.asarray(indptr, dtype=np.int64)
+        self.indices = np.asarray(indices, dtype=np.int64)
+        self.device = device
+        self.ok = True
+
+    def kind_table(self, value_arrays, diag_arrays):
+        """Device table [nkinds][K * maxnnz + 2] of a handle's values
+        (include/stk.h, stk_gs_fused), or None for generic programs."""
+        if self.rep is None:
+            return None
+        K = len(value_arrays)
+        tab = np.zeros((self.nkinds, K * self.maxnnz + 2))
+        for k, r in enumerate(self.rep):
+            # the order of the program's records: diagonal entry first
+            order = gs_program.diag_first(self.indptr, self.indices, r)
+            for j, v in enumerate(value_arrays):
+                tab[k, j:K * len(order):K] = np.asarray(v)[order]
+            for j, d in enumerate(diag_arrays):
+                tab[k, K * self.maxnnz + j] = d[r]
+        t = torch.from_numpy(tab).to(self.device)
+        self._keep.append(t)
+        return t
+
+    def sweeps(self, backward, K, tab, vals, diags, coefs, f, u_in, u_out):
+        """u_out <- the level's nu sweeps (device blocks); tests/microbench."""
+        v = [ptr(x) for x in vals] + [None] * (2 - len(vals))
+        d = [ptr(x) for x in diags] + [None] * (2 - len(diags))
+        c = [ptr(x) for x in coefs] + [None] * (2 - len(coefs))
+        check(lib().stk_gs_fused(self.handles[int(bool(backward))], K, self.T,
+                                 ptr(tab), self.nkinds, v[0], v[1], d[0], d[1],
+                                 c[0], c[1], ptr(f), ptr(u_in), ptr(u_out),
+                                 f.shape[1], stream()))
+
+    def attach(self, mg_handle, level, value_arrays, diag_arrays):
+        tab = self.kind_table(value_arrays, diag_arrays)
+        check(lib().stk_mg_set_fused(mg_handle, level, self.handles[0],
+                                     self.handles[1], ptr(tab), self.nkinds,
+                                     self.T))
+
+    def __del__(self):
+        try:
+            for h in self.handles:
+                lib().stk_gs_prog_destroy(h)
+            self.handles = []
+        except Exception:
+            pass
 
 
 def _project(pattern_keys, mat, ncols):
@@ -39,7 +161,7 @@ def _project(pattern_keys, mat, ncols):
     return vals
 
 
-def gauss_seidel_schedule(indptr, indices):
+def gauss_seidel_schedule(indptr, indices, return_wave=False):
     """Wavefronts of the lexicographic sweep: (rows ordered wavefront by
     wavefront, phase_ptr).  Host, setup only."""
     n = len(indptr) - 1
@@ -62,6 +184,8 @@ def gauss_seidel_schedule(indptr, indices):
     order = np.lexsort((maxcol, wave)).astype(np.int32)
     counts = np.bincount(wave, minlength=max(depth, 1))
     phase_ptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    if return_wave:
+        return order, phase_ptr, wave
     return order, phase_ptr
 
 
@@ -106,7 +230,7 @@ class MultiGridFamily:
     """All V-cycle preconditioners MG(sum_k c_k base_mats[k]) on one mesh
     hierarchy, K = len(base_mats) in {1, 2}."""
     def __init__(self, base_mats, hierarchy, smoothsteps=2, vcycles=1,
-                 device=None):
+                 device=None, ld_hint=None):
         self.K = K = len(base_mats)
         assert K in (1, 2)
         self.hierarchy = hierarchy
@@ -157,7 +281,8 @@ class MultiGridFamily:
             keys = rows * n + pat.indices
             vals = [_project(keys, mats[k][l], n) for k in range(K)]
             diags = [mats[k][l].diagonal() for k in range(K)]
-            order, phase_ptr = gauss_seidel_schedule(pat.indptr, pat.indices)
+            order, phase_ptr, wave = gauss_seidel_schedule(
+                pat.indptr, pat.indices, return_wave=True)
             self.num_phases.append(len(phase_ptr) - 1)
             d_indptr, d_indices = up(pat.indptr, np.int32), up(
                 pat.indices, np.int32)
@@ -169,10 +294,23 @@ class MultiGridFamily:
                 ptr(d_vals[0]), ptr(d_vals[1]) if K == 2 else None,
                 ptr(d_diag[0]), ptr(d_diag[1]) if K == 2 else None,
                 ptr(d_order), phase_ptr.ctypes.data, len(phase_ptr) - 1))
+            fused = None
+            if (l >= 1 and fused_enabled() and smoothsteps > 0
+                    and n >= FUSED_MIN_ROWS and len(phase_ptr) - 1 <= 8):
+                chunks = -(-(ld_hint or 256) // FUSED_T)
+                fused = FusedLevel(pat.indptr, pat.indices, wave, smoothsteps,
+                                   vals, diags, dev,
+                                   chunks=chunks,
+                                   sms=torch.cuda.get_device_properties(
+                                       dev).multi_processor_count)
+                if fused.ok:
+                    fused.attach(self.handle, l, vals, diags)
+                else:
+                    fused = None
             self._levels.append({
                 'n': n, 'vals': vals, 'diags': diags, 'indptr': d_indptr,
                 'indices': d_indices, 'order': d_order, 'phase_ptr': phase_ptr,
-                'transfer': None
+                'transfer': None, 'fused': fused
             })
             if l >= 1:
                 P = sp.csr_matrix(hierarchy.P_mats[l - 1], dtype=np.float64)
@@ -223,6 +361,8 @@ class MultiGridFamily:
                 if lv['transfer'] is not None:
                     check(lib().stk_mg_set_transfer(
                         h, l, *[ptr(t) for t in lv['transfer']]))
+                if lv['fused'] is not None:
+                    lv['fused'].attach(h, l, [vals], [diag])
             inv = torch.from_numpy(np.ascontiguousarray(
                 self.coarse_inverse(coefs))).to(self.device)
             keep.append(inv)

@@ -76,6 +76,29 @@ def main():
     timeit('gs 3 sweeps bwd finest (K=2)', lambda: check(lib().stk_mg_smooth(
         fam.handle, top, 3, 1, ptr(ctxK.coef[0]), ptr(ctxK.coef[1]), ptr(x.data), ptr(u), ld,
         stream())), 72)
+    fl = fam._levels[top].get('fused')
+    if fl is not None:
+        lvh = fam._levels[top]
+        print('fused program (fwd):', fl.programs[0].stats, flush=True)
+        tab2 = fl.kind_table(lvh['vals'], lvh['diags'])
+        dv = [torch.from_numpy(v).cuda() for v in lvh['vals']]
+        dd = [torch.from_numpy(np.ascontiguousarray(d)).cuda() for d in lvh['diags']]
+        u2 = torch.zeros_like(x.data)
+        timeit('FUSED gs 3 sweeps fwd zero-guess (K=2)', lambda: fl.sweeps(
+            False, 2, tab2, dv, dd, ctxK.coef, x.data, None, u2), 48)
+        timeit('FUSED gs 3 sweeps fwd (K=2)', lambda: fl.sweeps(
+            False, 2, tab2, dv, dd, ctxK.coef, x.data, u, u2), 72)
+        timeit('FUSED gs 3 sweeps bwd (K=2)', lambda: fl.sweeps(
+            True, 2, tab2, dv, dd, ctxK.coef, x.data, u, u2), 72)
+        a1 = lvh['vals'][1]
+        tab1 = fl.kind_table([a1], [lvh['diags'][1]])
+        timeit('FUSED gs 3 sweeps bwd (K=1)', lambda: fl.sweeps(
+            True, 1, tab1, [dv[1]], [dd[1]], [], x.data, u, u2), 72)
+    if args.only == 'fused':
+        timeit('MG K_x apply (2 V(3,3))', lambda: heq.Kinv_x.apply_block(x.data, y.data), 523)
+        timeit('S apply', lambda: heq.S._matvec(x, y), 1300)
+        timeit('P apply', lambda: heq.P._matvec(x, y), 1100)
+        return
     if args.only in ('gs', 'synth'):
         import scipy.sparse as sp
         from spacetime_fullgrid_parallel_b200.linop import DeviceCSR

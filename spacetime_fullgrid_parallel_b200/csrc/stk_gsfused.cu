@@ -7,7 +7,8 @@
 // window lives in shared memory (up to ~200 KB), the CTA walks the item's
 // macro-steps, and per macro-step
 //   1. issues the cp.async loads that bring rows into free window slots
-//      LOOKAHEAD steps before their first use,
+//      LOOKAHEAD steps before their first use (the program itself streams in
+//      through a ring of TMA bulk copies, one per pass of 128 row updates),
 //   2. runs the step's row updates  u_i += (f_i - A_i . u) / a_ii  with every
 //      operand u_j read from the window (LPO lanes per row, one double2 of
 //      time values per lane), storing final values of the item's own rows,
@@ -25,12 +26,14 @@
 namespace stk {
 
 constexpr int GS_LOOKAHEAD = 2;  // must equal gs_program.LOOKAHEAD
-constexpr int GS_PREFETCH = 4;   // must equal gs_program.PREFETCH
+constexpr int GS_RING = 8;       // pass slots of the record ring (>= 2 * GS_MAXPASS + 2)
+constexpr int GS_FRING = 4;      // passes between requesting an op's f and using it (= gs_program.PREFETCH)
+constexpr int GS_MAXPASS = 3;    // passes per macro-step the host may emit (gs_program.MAX_PASSES)
 
 struct GsArgs {
     const int *item_step, *item_pass;
     const int2 *step_info;  // per macro-step: (end pass, end load), global
-    const uint4 *rec;       // recq uint4 per record (gs_program.GSProgram)
+    const uint4 *rec;       // [npasses][recq][ngrp] uint4 (gs_program.GSProgram)
     int recq;
     const int2 *lds;  // window loads: (row, window slot)
     const double *ktab;  // [nkinds][K * maxnnz + 2]
@@ -53,6 +56,41 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
+__device__ __forceinline__ unsigned smem_u32(const void *p) {
+    return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(void *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(void *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+// TMA bulk copy global -> shared, completion counted on an mbarrier (UBLKCP).
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, unsigned bytes,
+                                             void *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void *bar, unsigned parity) {
+    const unsigned addr = smem_u32(bar);
+    unsigned done = 0, spins = 0;
+    while (true) {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            " selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) break;
+        if (++spins > (1u << 24)) __trap();  // a lost copy must not hang the GPU
+    }
+}
 __host__ __device__ __forceinline__ unsigned gs_table_stride(int K, int kstride) {
     if (K == 2) return ((kstride / 2) & 1) ? kstride : kstride + 2;
     return (kstride & 1) ? kstride : kstride + 1;
@@ -63,7 +101,8 @@ __device__ __forceinline__ unsigned slot_of(const uint4 &w, int q) {
 }
 
 // Shared memory: window [nslots][T] | value table | reciprocal diagonals |
-// record ring [PD][NGRP] x 32 B | f ring [PD][NGRP][T].
+// record ring [GS_RING][recq][NGRP] x 16 B | GS_RING mbarriers | f ring
+// [GS_FRING][NGRP][T].
 //   kinds, K = 1: the kind table as it is (values, diagonal, 1/diagonal)
 //   kinds, K = 2: the kind table as it is ((v0, v1) pairs, one broadcast read
 //                 per entry) and rdiag[kind][T] = 1 / (c0(t) e0 + c1(t) e1)
@@ -75,17 +114,20 @@ __device__ __forceinline__ unsigned slot_of(const uint4 &w, int q) {
 // Programs with row kinds list a row's entries diagonal first and padded to
 // NNZ entries (7 or 8) with zero-valued ones, so the row product is a fixed,
 // branch-free sequence; generic programs walk the CSR row (NNZ = 0).
-// Every global operand of an op (its record, its right-hand side) is copied
-// into the rings with cp.async PD passes before the op runs -- the program's
-// static pass layout gives those addresses in advance -- and completion is
-// tracked by cp.async groups (one per pass): register prefetch does not work
-// here, the counting scoreboards make a wait on an old load wait for the
-// newest one too (measured: profiles/r2_experiments.md).
+// The program is a stream: one thread feeds a ring of GS_RING pass slots with
+// TMA bulk copies (one contiguous copy per pass of NGRP records, completion on
+// the slot's mbarrier), refilling after each macro-step's barrier, when every
+// warp is done with the passes before it.  The right-hand side f of an op is a
+// scattered 64-byte piece: it comes through a per-group cp.async ring, requested
+// GS_FRING passes ahead (the record names that pass's row) and tracked by
+// cp.async groups, one per pass.  Register prefetch was measured and does not
+// work here: one pass ahead does not cover the latency, and deeper prefetches
+// share a counting scoreboard, so a wait on the oldest load waits for the
+// newest one too (profiles/r2_experiments.md).
 template <int LPO, int K, bool GEN, int NT, int NNZ>
 __global__ void __launch_bounds__(NT, 1) k_gs_fused(const GsArgs a) {
     constexpr int T = 2 * LPO;
     constexpr int NGRP = NT / LPO;
-    constexpr int PD = GS_PREFETCH;
     extern __shared__ __align__(16) double smem[];
     double *win = smem;
     double *vtab = win + (size_t)a.nslots * T;
@@ -96,9 +138,10 @@ __global__ void __launch_bounds__(NT, 1) k_gs_fused(const GsArgs a) {
     constexpr unsigned RS = T + 2;
     const unsigned tabsz = (unsigned)a.nkinds * ks + (K == 2 ? (unsigned)a.nkinds * RS : 0u);
     double *rdiag = vtab + (size_t)a.nkinds * ks;  // K == 2 only: [nkinds][RS]
-    uint4 *hring = reinterpret_cast<uint4 *>(vtab + ((tabsz + 1u) & ~1u));  // [PD][NGRP] headers
-    uint4 *nring = hring + PD * NGRP;                                        // [PD][NGRP] slots
-    double *fring = reinterpret_cast<double *>(nring + PD * NGRP);           // [PD][NGRP][T]
+    uint4 *ring = reinterpret_cast<uint4 *>(vtab + ((tabsz + 1u) & ~1u));  // [RING][recq][NGRP]
+    const unsigned pass_q = (unsigned)NGRP * a.recq;                        // uint4 per pass
+    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(ring + GS_RING * pass_q);
+    double *fring = reinterpret_cast<double *>(mbar + GS_RING);  // [GS_FRING][NGRP][T]
 
     const int item = blockIdx.x / a.nchunks;
     const int chunk = blockIdx.x - item * a.nchunks;
@@ -138,32 +181,41 @@ __global__ void __launch_bounds__(NT, 1) k_gs_fused(const GsArgs a) {
     const bool zero_guess = (a.uin == nullptr);
     const size_t tcol = (size_t)t;
     const double *fcol = a.f + tcol;
-    // this thread's places in the rings (slot r adds r * NGRP entries)
-    uint4 *myh = hring + grp, *myn = nring + grp;
-    double *myf = fring + grp * T + woff;
-
-    // fetch the record of pass q and the f row `frow` into ring slot r
-    uint4 *myrec = (lane ? myn : myh);  // lanes 0 / 1 copy the two halves of a record
-    auto prefetch = [&](const uint4 *src, int r, unsigned frow) {
-        if (lane < 2) cp_async16(myrec + r * NGRP, src);
-        if (valid) cp_async16(myf + r * (NGRP * T), fcol + (size_t)frow * a.ld);
-    };
-    const size_t rec_pass = (size_t)NGRP * a.recq;  // uint4 per pass
-    const uint4 *pf_src = a.rec + ((size_t)p0 * NGRP + grp) * a.recq + (lane & 1);
-    // ---- prologue: the first PD passes, one cp.async group each ----
-    for (int k = 0; k < PD; ++k) {
-        if (p0 + k < p_last) {
-            const unsigned frow =
-                __ldg(reinterpret_cast<const unsigned *>(
-                    a.rec + ((size_t)(p0 + k) * NGRP + grp) * a.recq)) & 0x7fffffffu;
-            prefetch(pf_src, k, frow);
+    // ---- record ring: producer = thread 0 ----
+    if (threadIdx.x == 0) {
+        for (int r = 0; r < GS_RING; ++r) mbar_init(mbar + r, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    int issued = p0;  // next pass to copy (thread 0)
+    auto feed = [&](int consumed) {  // every pass < consumed has been read by all warps
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        while (issued < p_last && issued < consumed + GS_RING) {
+            const int r = (issued - p0) & (GS_RING - 1);
+            mbar_expect_tx(mbar + r, pass_q * 16u);
+            tma_bulk_g2s(ring + r * pass_q, a.rec + (size_t)issued * pass_q, pass_q * 16u,
+                         mbar + r);
+            ++issued;
         }
-        pf_src += rec_pass;
+    };
+    if (threadIdx.x == 0) feed(p0);
+    // ---- f ring: the first GS_FRING passes, one cp.async group each ----
+    double *myf = fring + grp * T + woff;
+    for (int k = 0; k < GS_FRING; ++k) {
+        if (valid && p0 + k < p_last) {
+            const unsigned frow = __ldg(&(a.rec + (size_t)(p0 + k) * pass_q + grp)->x) & 0x7fffffffu;
+            cp_async16(myf + k * (NGRP * T), fcol + (size_t)frow * a.ld);
+        }
         cp_async_commit();
     }
+    int fr = 0;  // f ring slot of the current pass
 
     auto issue_load = [&](const int2 &e) {
         double *dst = win + (unsigned)e.y * T + woff;
+        // the row's right-hand side is first needed a few steps from now: have it
+        // in L2 by then (one sector pair per row and chunk)
+        if (valid && lane == 0)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(fcol + (size_t)e.x * a.ld));
         if (zero_guess || !valid)
             *reinterpret_cast<double2 *>(dst) = make_double2(0.0, 0.0);
         else
@@ -174,7 +226,7 @@ __global__ void __launch_bounds__(NT, 1) k_gs_fused(const GsArgs a) {
     int2 info = __ldg(a.step_info + m0);
     int2 ldpf = make_int2(0, 0);
     if (ld_beg + grp < info.y) ldpf = __ldg(a.lds + ld_beg + grp);
-    int p = p0, r = 0;
+    int p = p0;
     __syncthreads();  // tables ready
 
     for (int m = m0; m < m1; ++m) {
@@ -187,18 +239,19 @@ __global__ void __launch_bounds__(NT, 1) k_gs_fused(const GsArgs a) {
         }
         if (info.y + grp < info_nx.y) ldpf = __ldg(a.lds + info.y + grp);
         if (p == info.x) cp_async_commit();  // no pass in this step: its own group
-        // 2. the passes of this step
+        // 2. the passes of this step (window loads join the first pass's group)
         for (; p < info.x; ++p) {
-            cp_async_wait<PD - 1>();  // the group that fetched pass p has landed
-            __syncwarp();
-            const uint4 h = myh[r * NGRP];
-            uint4 nb = myn[r * NGRP];
-            const double2 fv = *reinterpret_cast<const double2 *>(myf + r * (NGRP * T));
-            __syncwarp();  // everyone has read slot r before it is refilled
-            if (p + PD < p_last) prefetch(pf_src, r, h.y);
-            pf_src += rec_pass;
+            const int q = p - p0, r = q & (GS_RING - 1);
+            mbar_wait(mbar + r, (unsigned)(q / GS_RING) & 1u);
+            const uint4 *slot = ring + r * pass_q + grp;
+            const uint4 h = slot[0];
+            uint4 nb = slot[NGRP];
+            cp_async_wait<GS_FRING - 1>();  // this pass's f has landed (own copy)
+            const double2 fv = *reinterpret_cast<const double2 *>(myf + fr * (NGRP * T));
+            if (valid && p + GS_FRING < p_last)
+                cp_async16(myf + fr * (NGRP * T), fcol + (size_t)h.y * a.ld);
             cp_async_commit();
-            r = (r + 1 == PD) ? 0 : r + 1;
+            fr = (fr + 1 == GS_FRING) ? 0 : fr + 1;
             const int nnz = (int)(h.w >> 16);
             if (nnz == 0) continue;  // padding
             const unsigned row = h.x & 0x7fffffffu;
@@ -230,8 +283,7 @@ __global__ void __launch_bounds__(NT, 1) k_gs_fused(const GsArgs a) {
             } else {
                 const size_t voff = (size_t)h.z;
                 for (int base = 0; base < nnz; base += 8) {
-                    if (base)
-                        nb = __ldg(a.rec + ((size_t)p * NGRP + grp) * a.recq + 1 + (base >> 3));
+                    if (base) nb = slot[NGRP * (1 + (base >> 3))];
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         const int e = base + q;
@@ -281,10 +333,12 @@ __global__ void __launch_bounds__(NT, 1) k_gs_fused(const GsArgs a) {
             *reinterpret_cast<double2 *>(up) = uo;
             if (store && valid) stv2(a.uout + (size_t)row * a.ld + tcol, uo);
         }
-        // 3. every step commits >= 1 group, so all but the 2 newest groups
-        //    include the window loads issued LOOKAHEAD steps ago
+        // 3. every step commits >= 1 group, so all but the 2 newest groups include
+        //    the window loads issued LOOKAHEAD steps ago; publish the updates; the
+        //    record ring slots of this step's passes are free again
         cp_async_wait<GS_LOOKAHEAD>();
         __syncthreads();
+        if (threadIdx.x == 0) feed(p);
         ld_beg = info.y;
         info = info_nx;
     }
@@ -357,7 +411,8 @@ int gs_fused_run(const stk_gs_prog *pg, int K, int T, const double *ktab, int nk
                  (K == 2 ? (size_t)a.nkinds * (T + 2) : 0);
     tab = (tab + 1) & ~(size_t)1;
     size_t smem = sizeof(double) * ((size_t)pg->nslots * T + tab) +
-                  (size_t)GS_PREFETCH * pg->ngrp * (32 + 8 * T);
+                  (size_t)GS_RING * pg->ngrp * pg->recw * 4 + GS_RING * 8 +
+                  (size_t)GS_FRING * pg->ngrp * T * 8;
     if (smem > 227 * 1024) return fail(-1, "stk_gs_fused: window does not fit shared memory");
 #define STK_GSF(KK, GG, NN) launch_gs_fused<4, KK, GG, 512, NN>(a, pg->nitems, smem, s)
     if (pg->ngrp != 128)

@@ -34,7 +34,8 @@ from ._lib import lib
 
 LOOKAHEAD = 2          # macro-steps between issuing a window load and using it
 LAG = 2                # columns between consecutive stages of the pipeline
-PREFETCH = 4           # passes between fetching an op's record / f and running it
+PREFETCH = 4           # the record names the row of the op this many passes later
+MAX_PASSES = 3         # passes per macro-step (the kernel's record ring holds 8)
 MAX_STAGES = 48
 MAX_KINDS = 64
 
@@ -255,7 +256,10 @@ class GSProgram:
 
     items:    item_step[nitems + 1], item_pass[nitems + 1]: step / pass ranges
     steps:    step_info[nsteps, 2] = (end pass, end load) of every macro-step
-    records:  op[npasses * ngrp, recw] uint32, recw = 8 + 4 * ceil((maxnnz - 8) / 8);
+    records:  op: npasses x (recw / 4) x ngrp x 4 uint32 (per pass: word
+              quadruples 0 of all records, then quadruples 1, ...;
+              records_aos() gives [npasses * ngrp, recw]),
+              recw = 8 + 4 * ceil((maxnnz - 8) / 8);
               record pass * ngrp + g is run by thread group g in that pass:
                 [0] row | store << 31
                 [1] row of the record PREFETCH passes later (same g): its f
@@ -269,6 +273,11 @@ class GSProgram:
     """
     def __init__(self):
         self.stats = {}
+
+    def records_aos(self):
+        q = self.recw // 4
+        return (self.op.reshape(-1, q, self.ngrp, 4).transpose(0, 2, 1, 3)
+                .reshape(-1, self.recw))
 
 
 def stage_colours(D, nsweeps, backward):
@@ -477,7 +486,12 @@ def compile_program(indptr, indices, wave, nsweeps, backward, capacity,
         ahead = np.arange(tot, dtype=np.int64) + PREFETCH * ngrp
         rec[:, 1] = rec[np.minimum(ahead, tot - 1), 0] & np.uint32(0x7fffffff)
         rec[ahead >= tot, 1] = 0
-        recs.append(rec)
+        if passes.max(initial=0) > MAX_PASSES:
+            return None
+        # device layout: per pass, all headers, then all slot words (SoA), so
+        # that one bulk copy brings a pass and the reads are conflict-free
+        recs.append(rec.reshape(-1, ngrp, recw // 4, 4).transpose(0, 2, 1, 3)
+                    .reshape(-1, recw))
         ld_rows.append(region[r['ld_row']].astype(np.int32))
         ld_slots.append(slot[r['ld_row']].astype(np.uint16))
         npass += int(pass_loc[-1])

@@ -71,8 +71,9 @@ class FusedLevel:
         ngrp = FUSED_NGRP if ngrp is None else ngrp
         if capacity is None:
             # what the window may take: shared memory minus the value tables
-            # and the record / f rings (csrc/stk_gsfused.cu)
-            rings = gs_program.PREFETCH * ngrp * (32 + 8 * T)
+            # and the record ring (csrc/stk_gsfused.cu: GS_RING pass slots)
+            recw = 8 + 4 * max(0, (self.maxnnz - 8 + 7) // 8)
+            rings = 8 * ngrp * recw * 4 + 64 + gs_program.PREFETCH * ngrp * T * 8
             capacity = min(65535, (FUSED_SMEM - tab_bytes - rings) // (8 * T))
         n = len(indptr) - 1
         emb = gs_program.graph_embedding(

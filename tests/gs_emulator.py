@@ -19,7 +19,7 @@ def emulate(prog, indptr, data, diag, f, u_in, check_hazards=True,
     n, k = f.shape
     u_out = np.full((n, k), np.nan)
     nnz_row = np.diff(indptr)
-    op = prog.op
+    op = prog.records_aos()
     G = prog.ngrp
     for it in range(prog.nitems):
         win = np.full((prog.nslots, k), np.nan)

@@ -13,8 +13,21 @@ reference classes, fed with `SquareProblem` matrices.
 import os
 import sys
 
-REFERENCE_ROOT = os.environ.get('STK_REFERENCE_ROOT', '/root/reference')
 _HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _root():
+    """The reference tree: $STK_REFERENCE_ROOT, /root/reference (the build
+    container), else the verbatim copy oracle/fetch_ref.py left in oracle/_ref
+    (what the GPU box has)."""
+    for cand in (os.environ.get('STK_REFERENCE_ROOT'), '/root/reference',
+                 os.path.join(_HERE, '_ref')):
+        if cand and os.path.isdir(os.path.join(cand, 'source')):
+            return cand
+    return '/root/reference'
+
+
+REFERENCE_ROOT = _root()
 
 
 def available():

@@ -323,13 +323,14 @@ def _tilings(embedding, per_col, S):
 
 def compile_program(indptr, indices, wave, nsweeps, backward, capacity,
                     embedding=None, kind_of_row=None, chunks=33, sms=148,
-                    max_redundancy=1.7, ngrp=128, verbose=False):
+                    max_redundancy=1.7, ngrp=128, tiling=None, verbose=False):
     """Program for `nsweeps` sweeps (forward or backward) of the level whose
     sparsity pattern is (indptr, indices) and whose rows have wavefront numbers
     `wave`.  `capacity` = window slots available to a CTA, `ngrp` = row updates
     a CTA runs side by side (threads / lanes per row), `chunks` = time chunks
     per item the launch is expected to have (items x chunks CTAs share `sms`
-    SMs: the tiling is chosen for the shortest makespan).  Returns None if the
+    SMs: the tiling is chosen for the shortest makespan; `tiling` = (strips,
+    segments) of an earlier program of the same level skips the search).  Returns None if the
     level does not tile well (deep wavefront DAG, 3-D-like connectivity,
     disconnected graph): the caller keeps the per-wavefront kernels then."""
     n = len(indptr) - 1
@@ -378,13 +379,23 @@ def compile_program(indptr, indices, wave, nsweeps, backward, capacity,
 
     max_seg = max(1, ncols // (4 * LAG * S + 1))  # shorter segments are all fill and drain
 
-    def try_tiling(nstrips, nseg):
+    def probe_tiling(nstrips, nseg):
+        """Schedule only the largest item: (makespan estimate, items) or None
+        if it does not fit the window."""
         its = items_for(nstrips, nseg)
-        probe = max(its, key=len)
-        res = _schedule_item(indptr, indices, wave, colours, probe, colidx,
-                             scratch)
+        res = _schedule_item(indptr, indices, wave, colours, max(its, key=len),
+                             colidx, scratch)
         if res['nslots'] > capacity:
             return None
+        per_step = (np.bincount(res['op_step']) + ngrp - 1) // ngrp
+        if per_step.max() > MAX_PASSES:
+            return None
+        # CTA rounds x passes of the longest item: what one launch costs when
+        # every SM holds one CTA (items x chunks CTAs on `sms` SMs)
+        longest = int(per_step.sum()) + res['nsteps'] // 2
+        return -(-len(its) * chunks // sms) * longest, its
+
+    def full_tiling(its):
         sch = [
             _schedule_item(indptr, indices, wave, colours, own, colidx,
                            scratch) for own in its
@@ -393,37 +404,40 @@ def compile_program(indptr, indices, wave, nsweeps, backward, capacity,
             return None
         return sch
 
-    def makespan(sch):
-        """CTA rounds x passes of the longest item: what one launch costs when
-        every SM holds one CTA (items x chunks CTAs on `sms` SMs)."""
-        longest = max(
-            int(((np.bincount(r['op_step']) + ngrp - 1) // ngrp).sum()) +
-            r['nsteps'] // 2 for r in sch)
-        return -(-len(sch) * chunks // sms) * longest
-
     sched = None
-    for _attempt in range(60):
-        sched = try_tiling(nstrips, 1)
-        if sched is not None:
-            break
-        if nstrips >= vmax:
+    if tiling is not None:
+        sched = full_tiling(items_for(*tiling))
+        nstrips = tiling[0]
+    else:
+        first = None
+        for _attempt in range(60):
+            first = probe_tiling(nstrips, 1)
+            if first is not None or nstrips >= vmax:
+                break
+            nstrips += 1 + nstrips // 16
+        if first is None:
             return None
-        nstrips += 1 + nstrips // 16
-    if sched is None:
-        return None
-    if nstrips > 1 or max_seg > 1:
         # more strips / segments: fuller passes of `ngrp` ops, fewer idle SMs
         # in the last round of CTAs
-        best = makespan(sched)
+        cands = [(first[0], nstrips, 1, first[1])]
         for ns in range(nstrips, nstrips + (4 if nstrips > 1 else 1)):
             for nseg in range(1, max_seg + 1):
-                if ns == nstrips and nseg == 1:
+                if (ns, nseg) == (nstrips, 1):
                     continue
                 if ns * nseg * chunks > 12 * sms and nseg > 1:
                     break
-                cand = try_tiling(ns, nseg)
-                if cand is not None and makespan(cand) < best:
-                    sched, best = cand, makespan(cand)
+                got = probe_tiling(ns, nseg)
+                if got is not None:
+                    cands.append((got[0], ns, nseg, got[1]))
+        cands.sort(key=lambda c: c[:3])
+        for _cost, ns, nseg, its in cands[:3]:
+            sched = full_tiling(its)
+            if sched is not None:
+                tiling = (ns, nseg)
+                nstrips = ns
+                break
+    if sched is None:
+        return None
     nops = sum(len(r['op_row']) for r in sched)
     redundancy = nops / float(n * nsweeps)
     if redundancy > max_redundancy:
@@ -513,6 +527,7 @@ def compile_program(indptr, indices, wave, nsweeps, backward, capacity,
     prog.nsweeps, prog.backward, prog.D = nsweeps, bool(backward), D
     prog.maxnnz, prog.recw, prog.ngrp = maxnnz, recw, ngrp
     prog.generic = kind_of_row is None
+    prog.tiling = tiling
     prog.stats = {
         'rows': n, 'items': len(sched), 'stages': S,
         'columns': ncols, 'ops': int(nops), 'redundancy': redundancy,

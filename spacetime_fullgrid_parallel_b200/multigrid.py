@@ -86,8 +86,8 @@ class FusedLevel:
             pg = gs_program.compile_program(
                 indptr, indices, wave, nsweeps, backward, capacity,
                 embedding=emb, kind_of_row=self.kind_of_row,
-                chunks=chunks, sms=sms,
-                ngrp=ngrp)
+                chunks=chunks, sms=sms, ngrp=ngrp,
+                tiling=progs[0].tiling if progs else None)
             if pg is None:
                 return
             progs.append(pg)

@@ -11,7 +11,7 @@ from conftest import ROOT
 def test_reference_arm_json_line():
     out = subprocess.run(
         [sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference',
-         '--steps', '1', '--warmup', '1'],
+         '--steps', '1', '--warmup', '1', '--J_space', '6'],
         capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.startswith('{')]
@@ -22,7 +22,13 @@ def test_reference_arm_json_line():
     assert d['higher_is_better'] is True and d['value'] > 0
     assert d['steps'] == 1 and d['warmup'] == 1 and d['n_gpus'] == 1
     assert d['config']['workload'].startswith('BASELINE.json configs[3]')
-    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
+    # the unmodified reference classes (oracle/_ref, copied by build()) when
+    # present, else the oracle port; the sample is stated, not implied
+    assert d['cpu_baseline']['kind'] in ('reference', 'port')
+    assert d['cpu_baseline']['cores'] >= 1
+    smp = d['config']['sample']
+    assert smp['J_space'] == 6 and smp['J_time'] <= d['config']['J_time']
+    assert smp['ranks'] == d['cpu_baseline']['cores']
     assert d['e2e'] == {'value': d['value'], 'unit': d['unit'],
                         'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
 

@@ -13,6 +13,7 @@ reference's mean.  Added: achieved algorithmic GB/s per operator.
 """
 import numpy as np
 
+from . import comm as stk_comm
 from .comm import Wtime
 from .heateq_mpi import mem
 from .mpi_kron import LinearOperatorMPI
@@ -69,7 +70,7 @@ def main(argv=None):
         print('Memory after construction: {}mb.'.format(mem()))
     data['mem_after_construction'] = mem()
 
-    LinearOperatorMPI.sync_timing = True
+    stk_comm.SYNC_TIMING = True
     comm.Barrier()
     t0 = Wtime()
     vec = KronVectorMPI(heq.dofs_distr)
@@ -83,7 +84,7 @@ def main(argv=None):
     comm.Barrier()
     data.update(time_total=Wtime() - t0, mem_after_timing=mem(),
                 gpu_mem_reserved_gb=torch.cuda.max_memory_reserved() / 1e9)
-    LinearOperatorMPI.sync_timing = False
+    stk_comm.SYNC_TIMING = False
     if rank == 0:
         print('')
         print('Completed {} iters steps.'.format(args.iters))

@@ -11,7 +11,8 @@ import scipy.sparse as sp
 import torch
 
 from ._lib import check, lib, ptr, stream
-from .comm import Wtime
+from . import comm as _comm
+from .comm import Wtime_device as Wtime
 from .linop import CompositeLinOp, as_space_op
 from .mpi_vector import KronVectorMPI, pitch
 from .timeop import TimeOpPlan
@@ -25,11 +26,11 @@ def as_matrix(operator):
 class LinearOperatorMPI:
     """Base class (mpi_kron.py:13-59).
 
-    Kernels are enqueued asynchronously, so by default `time_applies` counts
-    host time only.  Set `LinearOperatorMPI.sync_timing = True` (the timing
-    driver does) to bracket every `@` with a device synchronisation and get the
-    reference's meaning: wall time until the result exists."""
-    sync_timing = False
+    Kernels are enqueued asynchronously: `time_applies` and
+    `time_communication` have the reference's meaning (wall time until the
+    result exists) only while `comm.SYNC_TIMING` is on, which the drivers that
+    report them (heateq_mpi.main, heateq_mpi_timing) do; otherwise they count
+    host enqueue time."""
 
     def __init__(self, dofs_distr):
         self.dofs_distr = dofs_distr
@@ -41,12 +42,8 @@ class LinearOperatorMPI:
 
     def __matmul__(self, x):
         assert isinstance(x, KronVectorMPI)
-        if LinearOperatorMPI.sync_timing:
-            torch.cuda.synchronize()
         start = Wtime()
         y = self._matvec(x, x.empty_like())
-        if LinearOperatorMPI.sync_timing:
-            torch.cuda.synchronize()
         self.num_applies += 1
         self.time_applies += Wtime() - start
         return y

@@ -312,8 +312,8 @@ class TimeOpPlan2:
 
 
 def _now():
-    import time
-    return time.perf_counter()
+    from .comm import Wtime_device
+    return Wtime_device()
 
 
 _neighbour_plans = {}

@@ -126,5 +126,5 @@ def test_timing_driver_report_and_blob(monkeypatch, capsys):
         assert {'time_applies', 'time_communication', 'time_applies_iter',
                 'time_communication_iter', 'num_applies', 'time_total'} <= set(rec[name])
         assert rec[name]['num_applies'] == 3 and len(rec[name]['time_applies_iter']) == 3
-    from spacetime_fullgrid_parallel_b200.mpi_kron import LinearOperatorMPI
-    assert LinearOperatorMPI.sync_timing is False  # restored
+    from spacetime_fullgrid_parallel_b200 import comm as stk_comm
+    assert stk_comm.SYNC_TIMING is False  # restored

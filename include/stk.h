@@ -134,6 +134,16 @@ int stk_space_spmm_pair(int nrows, const int *indptr, const int *indices,
                         double alpha, double beta, const double *z, double *y,
                         int ld, void *stream);
 /* out[h*M + i] = x[i*ld + tidx[h]]   (pack time slices for a send). */
+/* out[i, c_out + c] = in[i, idx ? idx[c] : c_in + c], c < n, i < M: column
+ * gather / placement between blocks of pitches ld_in, ld_out (level-wise <->
+ * node order of wavelets.py:109-117; the piece placement of permute,
+ * mpi_vector.py:212-240).  in must not alias out. */
+int stk_copy_cols(int M, int n, const double *in, int ld_in, int c_in,
+                  const int *idx, double *out, int ld_out, int c_out,
+                  void *stream);
+/* x[i, t] = ux[i] * ut[t], t < ld (heateq_mpi.py:189-191: rhs = u0_t (x) u0_x). */
+int stk_outer(int M, int ld, const double *ux, const double *ut, double *x,
+              void *stream);
 int stk_pack_slices(const double *x, int ld, int M, const int *tidx, int n,
                     double *out, void *stream);
 /* x[i*ld + tidx[h]] = beta * x[...] + alpha * in[h*M + i]. */

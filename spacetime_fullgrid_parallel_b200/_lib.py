@@ -47,6 +47,9 @@ SIGNATURES = {
         _int, _vp, _vp, _vp, _vp, _vp, _vp, _int, _dbl, _dbl, _vp, _vp, _int,
         _vp
     ]),
+    'stk_copy_cols': (_int, [_int, _int, _vp, _int, _int, _vp, _vp, _int, _int,
+                             _vp]),
+    'stk_outer': (_int, [_int, _int, _vp, _vp, _vp, _vp]),
     'stk_pack_slices': (_int, [_vp, _int, _int, _vp, _int, _vp, _vp]),
     'stk_unpack_slices': (_int,
                           [_vp, _int, _int, _vp, _int, _vp, _dbl, _dbl, _vp]),

@@ -42,6 +42,11 @@ inline int check(cudaError_t e, const char *what) {
         if (_rc != 0) return _rc;  \
     } while (0)
 
+// The streaming kernels index (row, column-pair) items with 32-bit counters in
+// grid-stride loops: `k += stride` must not wrap, so the item count stays one
+// full grid (at most 2^21 threads) below 2^32.
+#define STK_MAX_ITEMS ((1ll << 32) - (1ll << 21))
+
 inline cudaStream_t as_stream(void *s) { return (cudaStream_t)s; }
 
 inline unsigned blocks_for(int64_t work, int threads) {

@@ -286,6 +286,36 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// out[i, c_out + c] = in[i, src(c)] for c < n: src(c) = idx[c] (a gather along
+// the time axis: level-wise <-> node order of wavelets.py:109-117) or c_in + c
+// (the piece placement of the time <-> space re-sharding, mpi_vector.py:
+// 212-240).  Threads walk c first: contiguous stores, near-contiguous loads.
+__global__ void __launch_bounds__(256)
+    k_copy_cols(int M, int n, const double *__restrict__ in, int ld_in, int c_in,
+                const int *__restrict__ idx, double *__restrict__ out, int ld_out, int c_out) {
+    const size_t total = (size_t)M * n;
+    const size_t stride = (size_t)gridDim.x * 256u;
+    for (size_t k = (size_t)blockIdx.x * 256u + threadIdx.x; k < total; k += stride) {
+        const size_t i = k / n;
+        const int c = (int)(k - i * n);
+        const int src = idx ? __ldg(idx + c) : c_in + c;
+        out[i * ld_out + c_out + c] = in[i * ld_in + src];
+    }
+}
+
+// x[i, t] = ux[i] * ut[t] (t < ld; ut holds zeros on the pads): the Kronecker
+// right-hand side of heateq_mpi.py:189-191.
+__global__ void __launch_bounds__(256)
+    k_outer(int M, int ld, const double *__restrict__ ux, const double *__restrict__ ut,
+            double *__restrict__ x) {
+    const size_t total = (size_t)M * ld;
+    const size_t stride = (size_t)gridDim.x * 256u;
+    for (size_t k = (size_t)blockIdx.x * 256u + threadIdx.x; k < total; k += stride) {
+        const size_t i = k / ld;
+        x[k] = __ldg(ux + i) * __ldg(ut + (k - i * ld));
+    }
+}
+
 __global__ void __launch_bounds__(256)
     k_pack_slices(const double *__restrict__ x, int ld, int M, const int *__restrict__ tidx,
                   int n, double *__restrict__ out) {
@@ -316,7 +346,7 @@ int launch_space_spmm(int nrows, const int *indptr, const int *indices, int K,
     if (nrows == 0) return 0;
     unsigned ld2 = (unsigned)ld / 2u;
     int64_t work = (int64_t)nrows * ld2;
-    if (work >= (1ll << 32)) return fail(-2, "stk_space_spmm: block too large for 32-bit grid");
+    if (work >= STK_MAX_ITEMS) return fail(-2, "stk_space_spmm: block too large for 32-bit grid");
     bool has_z = (beta != 0.0);
     if (has_z && z == nullptr) return fail(-1, "stk_space_spmm: beta != 0 needs z");
 #define STK_SPMM(KK, ZZ)                                                                     \
@@ -359,7 +389,7 @@ int stk_time_apply(int M, int nrows_t, int nnz, const int *indptr, const int *in
     if (M == 0) return 0;
     if (ldy & 1) return fail(-1, "stk_time_apply: pitch of y must be even");
     int64_t work = (int64_t)M * (ldy / 2);
-    if (work >= (1ll << 32)) return fail(-2, "stk_time_apply: block too large");
+    if (work >= STK_MAX_ITEMS) return fail(-2, "stk_time_apply: block too large");
     cudaStream_t s = as_stream(stream);
     // Dense-ish time matrices (> 4 nonzeros per row on average) go through the
     // shared-memory kernel when the matrix and a panel of >= 8 columns fit.
@@ -417,7 +447,7 @@ int stk_time_apply2(int M, int nrows_t, const int *indptr, const int *indices,
         return fail(-1, "stk_time_apply2: need nrows_t <= wy <= ldy, both even");
     if (M == 0) return 0;
     int64_t work = (int64_t)M * (wy / 2);
-    if (work >= (1ll << 32)) return fail(-2, "stk_time_apply2: block too large");
+    if (work >= STK_MAX_ITEMS) return fail(-2, "stk_time_apply2: block too large");
     cudaStream_t s = as_stream(stream);
     if (beta != 0.0)
         k_time_apply2<true><<<resident_grid(k_time_apply2<true>, 256, work), 256, 0, s>>>(
@@ -438,7 +468,7 @@ int stk_space_spmm_split(int nrows, const int *indptr, const int *indices, const
     if (nrows == 0) return 0;
     unsigned ld2 = (unsigned)ld / 2u;
     int64_t work = (int64_t)nrows * ld2;
-    if (work >= (1ll << 32)) return fail(-2, "stk_space_spmm_split: block too large");
+    if (work >= STK_MAX_ITEMS) return fail(-2, "stk_space_spmm_split: block too large");
     k_space_spmm_split<<<resident_grid(k_space_spmm_split, 256, work), 256, 0,
                          as_stream(stream)>>>(nrows, indptr, indices, vals0, vals1, x, y0, y1, ld,
                                               ld2);
@@ -456,7 +486,7 @@ int stk_space_spmm_pair(int nrows, const int *indptr, const int *indices, const 
     if (nrows == 0) return 0;
     unsigned ld2 = (unsigned)ld / 2u;
     int64_t work = (int64_t)nrows * ld2;
-    if (work >= (1ll << 32)) return fail(-2, "stk_space_spmm_pair: block too large");
+    if (work >= STK_MAX_ITEMS) return fail(-2, "stk_space_spmm_pair: block too large");
     cudaStream_t s = as_stream(stream);
     if (beta != 0.0)
         k_space_spmm_pair<true><<<resident_grid(k_space_spmm_pair<true>, 256, work), 256, 0, s>>>(
@@ -466,6 +496,24 @@ int stk_space_spmm_pair(int nrows, const int *indptr, const int *indices, const 
                                    s>>>(nrows, indptr, indices, vals0, vals1, x0, x1, ldx, alpha,
                                         beta, z, y, ld, ld2);
     return check_launch("k_space_spmm_pair");
+}
+
+int stk_copy_cols(int M, int n, const double *in, int ld_in, int c_in, const int *idx,
+                  double *out, int ld_out, int c_out, void *stream) {
+    if (M == 0 || n == 0) return 0;
+    if (in == out) return fail(-1, "stk_copy_cols: in must not alias out");
+    if (n < 0 || c_out < 0 || c_out + n > ld_out || (!idx && (c_in < 0 || c_in + n > ld_in)))
+        return fail(-1, "stk_copy_cols: column range outside the pitch");
+    k_copy_cols<<<resident_grid(k_copy_cols, 256, (int64_t)M * n), 256, 0, as_stream(stream)>>>(
+        M, n, in, ld_in, c_in, idx, out, ld_out, c_out);
+    return check_launch("k_copy_cols");
+}
+
+int stk_outer(int M, int ld, const double *ux, const double *ut, double *x, void *stream) {
+    if (M == 0 || ld == 0) return 0;
+    k_outer<<<resident_grid(k_outer, 256, (int64_t)M * ld), 256, 0, as_stream(stream)>>>(M, ld, ux,
+                                                                                       ut, x);
+    return check_launch("k_outer");
 }
 
 int stk_pack_slices(const double *x, int ld, int M, const int *tidx, int n, double *out,

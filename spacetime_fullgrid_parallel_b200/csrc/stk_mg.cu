@@ -225,7 +225,7 @@ static int smooth(const stk_mg *mg, int l, int nsweeps, bool backward, const dou
             int ph = backward ? nph - 1 - q : q;
             int r0 = lv.phase_ptr[ph], nr = lv.phase_ptr[ph + 1] - r0;
             if (nr == 0) continue;
-            if ((int64_t)nr * ld2 >= (1ll << 32)) return fail(-2, "stk_mg: block too large");
+            if ((int64_t)nr * ld2 >= STK_MAX_ITEMS) return fail(-2, "stk_mg: block too large");
             const bool first = zero_guess && sw == 0 && !backward;
 #define STK_GS(KK, FF)                                                                        \
     k_gs_phase<KK, FF><<<resident_grid(k_gs_phase<KK, FF>, 256, (int64_t)nr * ld2), 256, 0, s>>>( \

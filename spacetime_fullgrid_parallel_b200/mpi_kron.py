@@ -254,22 +254,30 @@ class MatKronIdentityMPI(LinearOperatorMPI):
                                              stream()))
                 return res
             else:
+                # level-wise ordering (wavelets.py:113-117): coefficient k
+                # lives at node pos[k]; gather along the time axis with the
+                # permutation or its inverse, lifting in between
                 if self._pos is None:
-                    self._pos = torch.from_numpy(
-                        levelwise_positions(op.J)).to(sblock.device)
+                    pos = levelwise_positions(op.J)
+                    inv = np.empty_like(pos)
+                    inv[pos] = np.arange(len(pos))
+                    self._pos = (torch.from_numpy(pos.astype(np.int32)).to(sblock.device),
+                                 torch.from_numpy(inv.astype(np.int32)).to(sblock.device))
+                pos, inv = self._pos
+                ldb = sblock.shape[1]
                 res = torch.zeros_like(sblock)
-                if not op.transposed:  # coefficients to their nodes
-                    res[:, self._pos] = sblock[:, :N]
-                else:
-                    res[:, :N] = sblock[:, :N]
-            check(lib().stk_wavelet_lift(res.shape[0], op.J,
-                                         int(op.transposed), ptr(res),
-                                         ptr(res), res.shape[1], stream()))
-            if not op.interleaved and op.transposed:
-                out = torch.zeros_like(res)
-                out[:, :N] = res[:, self._pos]
-                res = out
-            return res
+                if not op.transposed:  # coefficients to their nodes, then lift
+                    check(lib().stk_copy_cols(sblock.shape[0], N, ptr(sblock), ldb, 0,
+                                              ptr(inv), ptr(res), ldb, 0, stream()))
+                    check(lib().stk_wavelet_lift(res.shape[0], op.J, 0, ptr(res),
+                                                 ptr(res), ldb, stream()))
+                    return res
+                tmp = torch.empty_like(sblock)  # lift, then nodes to coefficients
+                check(lib().stk_wavelet_lift(res.shape[0], op.J, 1, ptr(sblock),
+                                             ptr(tmp), ldb, stream()))
+                check(lib().stk_copy_cols(sblock.shape[0], N, ptr(tmp), ldb, 0, ptr(pos),
+                                          ptr(res), ldb, 0, stream()))
+                return res
         if self._dev is None:
             dev = sblock.device
             self._dev = tuple(

@@ -189,7 +189,8 @@ class KronVectorMPI:
         ut = torch.zeros(self.ld, dtype=torch.float64, device=dev)
         ut[:self.n_loc] = torch.as_tensor(np.asarray(u_t_loc, dtype=np.float64))
         ux = torch.as_tensor(np.asarray(u_x, dtype=np.float64)).to(dev)
-        torch.outer(ux, ut, out=self.data)
+        check(lib().stk_outer(self.M, self.ld, ptr(ux), ptr(ut), ptr(self.data),
+                              stream()))
         return self
 
     def copy(self):

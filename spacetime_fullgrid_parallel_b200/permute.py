@@ -11,6 +11,7 @@ what stk_time_apply wants.  `PermutePlan` is host logic (CPU-testable).
 """
 import torch
 
+from ._lib import check, lib, ptr, stream
 from .mpi_vector import DofDistributionMPI, KronVectorMPI, pitch
 
 
@@ -35,9 +36,10 @@ class PermutePlan:
                         device=block.device) for ta, tb in self.t_bounds
         ]
         d.comm.all_to_all(sends, recvs)
-        for p, (ta, tb) in enumerate(self.t_bounds):
-            piece = recvs[p].view(self.m_loc, pitch(tb - ta))
-            out[:, ta:tb].copy_(piece[:, :tb - ta])
+        for p, (ta, tb) in enumerate(self.t_bounds):  # place the pieces
+            check(lib().stk_copy_cols(self.m_loc, tb - ta, ptr(recvs[p]),
+                                      pitch(tb - ta), 0, None, ptr(out),
+                                      self.ld_full, ta, stream()))
         return out
 
     def backward(self, sblock, n_loc, ld):
@@ -49,7 +51,9 @@ class PermutePlan:
         for pa, pb in self.t_bounds:
             piece = torch.zeros((self.m_loc, pitch(pb - pa)),
                                 dtype=sblock.dtype, device=sblock.device)
-            piece[:, :pb - pa].copy_(sblock[:, pa:pb])
+            check(lib().stk_copy_cols(self.m_loc, pb - pa, ptr(sblock),
+                                      sblock.shape[1], pa, None, ptr(piece),
+                                      pitch(pb - pa), 0, stream()))
             sends.append(piece.reshape(-1))
         recvs = [out[xa:xb].reshape(-1) for xa, xb in self.x_bounds]
         # out rows are contiguous, so the pieces land in place

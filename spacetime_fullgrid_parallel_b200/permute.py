@@ -15,8 +15,17 @@ from ._lib import check, lib, ptr, stream
 from .mpi_vector import DofDistributionMPI, KronVectorMPI, pitch
 
 
+def _device_copy_cols(src, c_in, n, dst, c_out):
+    """dst[:, c_out:c_out+n] = src[:, c_in:c_in+n] on device blocks (libstk)."""
+    check(lib().stk_copy_cols(src.shape[0], n, ptr(src), src.shape[1], c_in,
+                              None, ptr(dst), dst.shape[1], c_out, stream()))
+
+
 class PermutePlan:
-    def __init__(self, dofs_distr):
+    """`copy_cols(src, c_in, n, dst, c_out)` places pieces; the default is the
+    device kernel (the CPU tests of the plan's host logic pass a stand-in)."""
+    def __init__(self, dofs_distr, copy_cols=_device_copy_cols):
+        self.copy_cols = copy_cols
         d = self.dofs_distr = dofs_distr
         self.space_distr = DofDistributionMPI(d.comm, d.M, d.N)
         self.t_bounds = d.dof_distribution
@@ -37,9 +46,8 @@ class PermutePlan:
         ]
         d.comm.all_to_all(sends, recvs)
         for p, (ta, tb) in enumerate(self.t_bounds):  # place the pieces
-            check(lib().stk_copy_cols(self.m_loc, tb - ta, ptr(recvs[p]),
-                                      pitch(tb - ta), 0, None, ptr(out),
-                                      self.ld_full, ta, stream()))
+            self.copy_cols(recvs[p].view(self.m_loc, pitch(tb - ta)), 0,
+                           tb - ta, out, ta)
         return out
 
     def backward(self, sblock, n_loc, ld):
@@ -51,9 +59,7 @@ class PermutePlan:
         for pa, pb in self.t_bounds:
             piece = torch.zeros((self.m_loc, pitch(pb - pa)),
                                 dtype=sblock.dtype, device=sblock.device)
-            check(lib().stk_copy_cols(self.m_loc, pb - pa, ptr(sblock),
-                                      sblock.shape[1], pa, None, ptr(piece),
-                                      pitch(pb - pa), 0, stream()))
+            self.copy_cols(sblock, pa, pb - pa, piece, 0)
             sends.append(piece.reshape(-1))
         recvs = [out[xa:xb].reshape(-1) for xa, xb in self.x_bounds]
         # out rows are contiguous, so the pieces land in place

@@ -97,7 +97,10 @@ def _body(rank, size):
     ld = pitch(b - a)
     block = torch.zeros((M, ld), dtype=torch.float64)
     block[:, :b - a] = torch.from_numpy(X[a:b].T.copy())
-    pp = PermutePlan(d)
+    def host_copy_cols(src, c_in, n, dst, c_out):  # stand-in for stk_copy_cols
+        dst[:, c_out:c_out + n] = src[:, c_in:c_in + n]
+
+    pp = PermutePlan(d, copy_cols=host_copy_cols)
     sblock = pp.forward(block, b - a, ld)
     xa, xb = pp.space_distr.t_begin, pp.space_distr.t_end
     assert np.array_equal(sblock[:, :N].numpy(), X.T[xa:xb])

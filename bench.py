@@ -429,7 +429,8 @@ def run_stk(args):
                                args.gpus)
     dev = torch.cuda.current_device()
 
-    heq = HeatEquationMPI(J_space=args.J_space, J_time=args.J_time, comm=comm)
+    heq = HeatEquationMPI(J_space=args.J_space, J_time=args.J_time, comm=comm,
+                          order=args.order)
     D = heq.N * heq.M
     state = PCGState(heq)
 
@@ -467,7 +468,7 @@ def run_stk(args):
     top = len(fam.num_phases) - 1
     nph = fam.num_phases[top]
     ld = heq.rhs.ld
-    ctx = fam.context([(0.0, 1.0)], ld)
+    ctx = heq.P._chain[0][1]  # the groups of P: one matrix per wavelet level
     u = torch.zeros_like(heq.rhs.data)
     u2 = torch.empty_like(u)
     f = heq.rhs.data
@@ -477,17 +478,18 @@ def run_stk(args):
     traffic = None
     tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
     if fl is not None:
+        from spacetime_fullgrid_parallel_b200.multigrid import _project
         nu = fam.smoothsteps
-        tab = fl.kind_table(lvh['vals'], lvh['diags'])
-        dv = [torch.from_numpy(np.ascontiguousarray(v)).cuda() for v in lvh['vals']]
-        dd = [torch.from_numpy(np.ascontiguousarray(d)).cuda() for d in lvh['diags']]
+        vals = fl.values_for([
+            _project(lvh['keys'], fam._galerkin(fam.combined(g))[top],
+                     lvh['n'], lvh['pattern']) for g in ctx.groups])
 
         def sweeps():
-            fl.sweeps(True, 2, tab, dv, dd, ctx.coef, f, u, u2)
+            fl.sweeps(True, vals, ctx.group, f, u, u2)
 
-        kernel = ('k_gs_fused<4,2,false,512,7> (the %d backward Gauss-Seidel '
-                  'sweeps of the finest level in one launch, per-slice '
-                  'coefficients)' % nu)
+        kernel = ('k_gs_fused<4,true,false,512,7> (the %d backward Gauss-Seidel '
+                  'sweeps of the finest level in one launch, one matrix per '
+                  'wavelet level)' % nu)
         # G1 of SURVEY.md 8(d): 24 B per level-dof per sweep (u read, f read, u
         # written) x nu sweeps, n_loc live time slices per row
         bytes_per_launch = 24.0 * nu * heq.M * heq.rhs.n_loc
@@ -495,12 +497,11 @@ def run_stk(args):
         key = 'k_gs_fused_bytes_per_launch'
     else:
         def sweeps():
-            check(lib().stk_mg_smooth(fam.handle, top, 1, 0, ptr(ctx.coef[0]),
-                                      ptr(ctx.coef[1]), ptr(f), ptr(u), ld,
-                                      stream()))
+            check(lib().stk_mg_smooth(ctx.handle, top, 1, 0, ptr(ctx.group),
+                                      ptr(f), ptr(u), ld, stream()))
 
-        kernel = ('k_gs_phase4<2,false> (one Gauss-Seidel wavefront, finest '
-                  'level, per-slice coefficients)')
+        kernel = ('k_gs_phase<true,false> (one Gauss-Seidel wavefront, finest '
+                  'level, one matrix per wavelet level)')
         bytes_per_launch = 24.0 * heq.M * heq.rhs.n_loc / nph
         launches_per_rep = nph
         key = 'k_gs_phase_bytes_per_launch'
@@ -533,6 +534,7 @@ def run_stk(args):
     if args.no_e2e:  # profiling runs: skip the full solve and the CPU leg
         if rank == 0:
             print(json.dumps({'ms_per_step': ms_per_step, 'value': value,
+                              'order': args.order,
                               'gpu_launches': int(launches),
                               'roofline': roofline, 'note': 'profiling run'}),
                   flush=True)
@@ -604,6 +606,7 @@ def run_stk(args):
             'J_time': args.J_time, 'J_space': args.J_space, 'N': heq.N,
             'M': heq.M, 'dofs': D, 'smoothsteps': 3, 'vcycles': 2,
             'alpha': 0.3, 'wavelettransform': 'composite',
+            'order': args.order,
             'parallelism': 'time-slab x%d' % size,
             'l2': 'inputs larger than L2 (one vector = %.2f GB), no flush' %
             (8e-9 * D / size)
@@ -628,6 +631,9 @@ def main():
                     help='profiling runs: timed iterations and roofline only')
     ap.add_argument('--no-cpu', dest='no_cpu', action='store_true',
                     help='skip the cpu_baseline leg (profiling runs)')
+    ap.add_argument('--order', default='class',
+                    help="numbering of the new vertices of a level (assembly.py): "
+                    "'class' (4 Gauss-Seidel wavefronts), 'lex', 'random'")
     ap.add_argument('--no-config5', dest='no_config5', action='store_true',
                     help='at 8 GPUs: skip the J_time=10 J_space=10 solve')
     args = ap.parse_args()

@@ -176,21 +176,24 @@ int stk_time_chain(int M, int n_loc, int n_halo, int nlev, const int *lev_ptr,
 
 /* ---- multigrid V-cycle, batched over all time slices --------------------
  * multigrid.py:130-197 (MultiGrid), :100-127 (PETSc MatSOR sweeps).
- * A handle describes one Galerkin hierarchy (levels 0..nlevels-1, the last
- * one finest) by device pointers the caller keeps alive. */
+ * A handle describes the Galerkin hierarchies (levels 0..nlevels-1, the last
+ * one finest) of G matrices on one sparsity pattern by device pointers the
+ * caller keeps alive.  Every time slice t of a block belongs to one of the G
+ * GROUPS (group[t]) and is preconditioned with that group's hierarchy: G = 1
+ * is K_x = MG(A_x), G = J_time + 1 serves all C_j = MG(2^j M_x + alpha A_x) of
+ * heateq_mpi.py:143-153 in one launch sequence. */
 typedef struct stk_mg stk_mg;
-stk_mg *stk_mg_create(int nlevels, int smoothsteps, int vcycles, int K);
+stk_mg *stk_mg_create(int nlevels, int smoothsteps, int vcycles, int G);
 void stk_mg_destroy(stk_mg *mg);
-/* Level matrix (union pattern, K value arrays, K diagonals) and its
- * Gauss-Seidel schedule: sched_rows (device) lists the rows wavefront by
- * wavefront, phase_ptr (HOST, nphases+1 entries) delimits the wavefronts.
- * Rows inside a wavefront are mutually independent and every row comes after
- * all its lower-numbered neighbours, so running the wavefronts in order is
- * exactly the lexicographic sweep of multigrid.py:89-97 / MatSOR. */
-int stk_mg_set_level(stk_mg *mg, int level, int nrows, const int *indptr,
-                     const int *indices, const double *vals0,
-                     const double *vals1, const double *diag0,
-                     const double *diag1, const int *sched_rows,
+/* Level pattern, the G level matrices (vals: G x nnz in CSR order, diag:
+ * G x nrows) and the Gauss-Seidel schedule: sched_rows (device) lists the rows
+ * wavefront by wavefront, phase_ptr (HOST, nphases+1 entries) delimits the
+ * wavefronts.  Rows inside a wavefront are mutually independent and every row
+ * comes after all its lower-numbered neighbours, so running the wavefronts in
+ * order is exactly the lexicographic sweep of multigrid.py:89-97 / MatSOR. */
+int stk_mg_set_level(stk_mg *mg, int level, int nrows, int nnz,
+                     const int *indptr, const int *indices, const double *vals,
+                     const double *diag, const int *sched_rows,
                      const int *phase_ptr_host, int nphases);
 /* Prolongation level-1 -> level (CSR, nrows(level) x nrows(level-1)) and its
  * transpose (multigrid.py:39-60). */
@@ -200,19 +203,17 @@ int stk_mg_set_transfer(stk_mg *mg, int level, const int *p_indptr,
                         const double *r_vals);
 /* Doubles of workspace stk_mg_apply needs for blocks of pitch ld. */
 int64_t stk_mg_workspace(const stk_mg *mg, int ld);
-/* x <- `vcycles` V(nu,nu)-cycles for A(t) x = b from x = 0, every slice t of
- * the block at once.  coef0/coef1: per-slice coefficients (K = 2) or NULL.
- * coarse_inv: G dense inverses (n0 x n0, row-major) of the coarsest matrix;
- * coarse_group[t] selects the one of slice t (NULL: group 0 for all). */
-int stk_mg_apply(stk_mg *mg, const double *coef0, const double *coef1,
-                 const double *coarse_inv, const int *coarse_group,
-                 const double *b, double *x, int ld, double *ws,
-                 void *stream);
-/* One family of Gauss-Seidel sweeps on a level (exposed for tests):
- * `nsweeps` forward (backward = 0) or backward sweeps of u on level. */
+/* x <- `vcycles` V(nu,nu)-cycles for A_{group[t]} x = b from x = 0, every slice
+ * t of the block at once.  group: int[ld] (pads repeat the last slice's group)
+ * or NULL when G = 1.  coarse_inv: G dense inverses (n0 x n0, row-major) of
+ * the coarsest matrices. */
+int stk_mg_apply(stk_mg *mg, const int *group, const double *coarse_inv,
+                 const double *b, double *x, int ld, double *ws, void *stream);
+/* One family of Gauss-Seidel sweeps on a level with the per-wavefront kernels
+ * (exposed for tests): `nsweeps` forward (backward = 0) or backward sweeps. */
 int stk_mg_smooth(stk_mg *mg, int level, int nsweeps, int backward,
-                  const double *coef0, const double *coef1, const double *f,
-                  double *u, int ld, void *stream);
+                  const int *group, const double *f, double *u, int ld,
+                  void *stream);
 
 /* HOST helper (host pointers): wave[i] = wavefront of row i in the
  * lexicographic Gauss-Seidel dependency DAG of a symmetric-pattern CSR matrix
@@ -240,24 +241,24 @@ stk_gs_prog *stk_gs_prog_create(int nitems, int nslots, int maxnnz, int generic,
                                 const void *rec, const void *ld);
 void stk_gs_prog_destroy(stk_gs_prog *prog);
 /* u_out <- the program's sweeps applied to u_in (NULL: zero initial guess) with
- * right-hand side f; u_in must not alias u_out.  T = time values per CTA (8).  Matrix values: the kind table ktab[nkinds][K*maxnnz + 2] (per kind:
- * K = 1: values, diagonal, spare; K = 2: (v0, v1) pairs, then the two
- * diagonals) for programs compiled with row kinds, else the level's CSR value
- * arrays v0/v1 and diagonals d0/d1.  coef0/coef1: per-slice coefficients
- * (K = 2). */
-int stk_gs_fused(const stk_gs_prog *prog, int K, int T, const double *ktab,
-                 int nkinds, const double *v0, const double *v1,
-                 const double *d0, const double *d1, const double *coef0,
-                 const double *coef1, const double *f, const double *u_in,
-                 double *u_out, int ld, void *stream);
-/* Attach the fused smoother programs (nu forward / nu backward sweeps) and the
- * kind table of this handle's values to a level of a multigrid hierarchy;
- * stk_mg_apply then runs each smoothing phase of that level as one launch
- * (and needs one more block of workspace per fused level, see
- * stk_mg_workspace).  Call before the first stk_mg_apply. */
+ * right-hand side f; u_in must not alias u_out.  T = time values per CTA (8).
+ * Matrix values of the G groups, entries in the program's order (diagonal
+ * first): for programs compiled with row kinds the table
+ * ktab[G][nkinds][maxnnz + 2] (bulk_kind = the kind most rows have: its values
+ * are kept in registers), else cvals[G][vstride] (values of every row at its
+ * CSR offset).  group: int[ld] or NULL when G = 1. */
+int stk_gs_fused(const stk_gs_prog *prog, int G, int T, const double *ktab,
+                 int nkinds, int bulk_kind, const double *cvals,
+                 int64_t vstride, const int *group, const double *f,
+                 const double *u_in, double *u_out, int ld, void *stream);
+/* Attach the fused smoother programs (nu forward / nu backward sweeps) and this
+ * handle's values in program order to a level; stk_mg_apply then runs each
+ * smoothing phase of that level as one launch (and needs one more block of
+ * workspace per fused level, see stk_mg_workspace).  Call before the first
+ * stk_mg_apply. */
 int stk_mg_set_fused(stk_mg *mg, int level, const stk_gs_prog *fwd,
                      const stk_gs_prog *bwd, const double *ktab, int nkinds,
-                     int T);
+                     int bulk_kind, const double *cvals, int T);
 /* HOST helper (host pointers): interval colouring of window lifetimes
  * [start[q], end[q]] (macro-steps); slot[q] out; returns the slots used. */
 int stk_gs_alloc_slots(int n, const int *start, const int *end, int *slot);

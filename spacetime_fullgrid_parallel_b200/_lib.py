@@ -61,25 +61,23 @@ SIGNATURES = {
     'stk_mg_create': (_vp, [_int, _int, _int, _int]),
     'stk_mg_destroy': (None, [_vp]),
     'stk_mg_set_level': (_int, [
-        _vp, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int
+        _vp, _int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _int
     ]),
     'stk_mg_set_transfer': (_int, [_vp, _int, _vp, _vp, _vp, _vp, _vp, _vp]),
     'stk_mg_workspace': (_i64, [_vp, _int]),
-    'stk_mg_apply': (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _vp,
-                            _vp]),
-    'stk_mg_smooth': (_int, [
-        _vp, _int, _int, _int, _vp, _vp, _vp, _vp, _int, _vp
-    ]),
+    'stk_mg_apply': (_int, [_vp, _vp, _vp, _vp, _vp, _int, _vp, _vp]),
+    'stk_mg_smooth': (_int, [_vp, _int, _int, _int, _vp, _vp, _vp, _int, _vp]),
     'stk_gs_wavefronts': (_int, [_int, _vp, _vp, _vp]),
     'stk_gs_alloc_slots': (_int, [_int, _vp, _vp, _vp]),
     'stk_gs_prog_create': (_vp, [
         _int, _int, _int, _int, _int, _int, _vp, _vp, _vp, _vp, _vp
     ]),
     'stk_gs_prog_destroy': (None, [_vp]),
-    'stk_mg_set_fused': (_int, [_vp, _int, _vp, _vp, _vp, _int, _int]),
+    'stk_mg_set_fused': (_int, [_vp, _int, _vp, _vp, _vp, _int, _int, _vp,
+                                _int]),
     'stk_gs_fused': (_int, [
-        _vp, _int, _int, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-        _vp, _int, _vp
+        _vp, _int, _int, _vp, _int, _int, _vp, _i64, _vp, _vp, _vp, _vp, _int,
+        _vp
     ]),
 }
 

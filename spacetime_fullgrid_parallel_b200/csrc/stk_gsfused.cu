@@ -36,10 +36,12 @@ struct GsArgs {
     const uint4 *rec;       // [npasses][recq][ngrp] uint4 (gs_program.GSProgram)
     int recq;
     const int2 *lds;  // window loads: (row, window slot)
-    const double *ktab;  // [nkinds][K * maxnnz + 2]
-    int nkinds, kstride, maxnnz, nslots;
-    const double *v0, *v1, *d0, *d1;  // generic path: CSR values, diagonals
-    const double *coef0, *coef1;
+    // matrix values: one matrix per GROUP of time slices, grp[t] = group of t
+    const double *ktab;  // kinds: [G][nkinds][maxnnz + 2], entries in program order
+    int G, nkinds, kstride, maxnnz, nslots, bulk_kind;
+    const double *cvals;  // generic: [G][vstride] values in program entry order
+    size_t vstride;
+    const int *grp;
     const double *f, *uin;
     double *uout;
     int ld, nchunks;
@@ -91,8 +93,9 @@ __device__ __forceinline__ void mbar_wait(void *bar, unsigned parity) {
         if (++spins > (1u << 24)) __trap();  // a lost copy must not hang the GPU
     }
 }
-__host__ __device__ __forceinline__ unsigned gs_table_stride(int K, int kstride) {
-    if (K == 2) return ((kstride / 2) & 1) ? kstride : kstride + 2;
+// shared-memory stride of a kind's value row: an odd number of doubles, so that
+// different (group, kind) rows fall into different banks
+__host__ __device__ __forceinline__ unsigned gs_table_stride(int kstride) {
     return (kstride & 1) ? kstride : kstride + 1;
 }
 __device__ __forceinline__ unsigned slot_of(const uint4 &w, int q) {
@@ -103,17 +106,18 @@ __device__ __forceinline__ unsigned slot_of(const uint4 &w, int q) {
 // Shared memory: window [nslots][T] | value table | reciprocal diagonals |
 // record ring [GS_RING][recq][NGRP] x 16 B | GS_RING mbarriers | f ring
 // [GS_FRING][NGRP][T].
-//   kinds, K = 1: the kind table as it is (values, diagonal, 1/diagonal)
-//   kinds, K = 2: the kind table as it is ((v0, v1) pairs, one broadcast read
-//                 per entry) and rdiag[kind][T] = 1 / (c0(t) e0 + c1(t) e1)
-//                 for THIS chunk's time values.  (A per-chunk table of the
-//                 combined values c0 v0 + c1 v1 costs one FMA less per entry
-//                 but four shared-memory wavefronts more per warp, and the
-//                 kernel is bound by shared-memory bandwidth: measured.)
-//   generic: nothing (values come from the CSR arrays through L1/L2)
-// Programs with row kinds list a row's entries diagonal first and padded to
-// NNZ entries (7 or 8) with zero-valued ones, so the row product is a fixed,
-// branch-free sequence; generic programs walk the CSR row (NNZ = 0).
+// Matrix values.  Every time slice belongs to a group g(t) with its own matrix
+// on the shared pattern (GROUPED; one group otherwise).  A program lists a
+// row's entries in canonical order (diagonal first, then sorted by value), so
+// rows of a uniformly refined mesh fall into a handful of KINDS with identical
+// value sequences, and one of them -- the interior stencil -- covers almost
+// every row:
+//   kinds:   vtab[g][kind][entry] in shared memory; the BULK kind's values for
+//            this lane's two time values live in registers (no shared-memory
+//            read per entry for ~all ops); rdiag[kind][T] = 1 / diagonal
+//   generic: cvals[g][csr offset + entry] through L1/L2, a division per update
+// Programs with kinds pad rows to NNZ entries (7 or 8) with zero-valued ones:
+// the row product is a fixed, branch-free sequence.
 // The program is a stream: one thread feeds a ring of GS_RING pass slots with
 // TMA bulk copies (one contiguous copy per pass of NGRP records, completion on
 // the slot's mbarrier), refilling after each macro-step's barrier, when every
@@ -124,22 +128,22 @@ __device__ __forceinline__ unsigned slot_of(const uint4 &w, int q) {
 // work here: one pass ahead does not cover the latency, and deeper prefetches
 // share a counting scoreboard, so a wait on the oldest load waits for the
 // newest one too (profiles/r2_experiments.md).
-template <int LPO, int K, bool GEN, int NT, int NNZ>
+template <int LPO, bool GROUPED, bool GEN, int NT, int NNZ>
 __global__ void __launch_bounds__(NT, 1) k_gs_fused(const GsArgs a) {
     constexpr int T = 2 * LPO;
     constexpr int NGRP = NT / LPO;
+    constexpr bool BULK = !GEN && NNZ > 0;  // bulk kind's values in registers
+    constexpr int NB = BULK ? NNZ : 1;
     extern __shared__ __align__(16) double smem[];
     double *win = smem;
     double *vtab = win + (size_t)a.nslots * T;
-    // table strides padded so that different kinds fall into different banks
-    // (K = 2: 16-byte pairs, an odd number of them per kind; K = 1: an odd
-    // number of doubles; reciprocal diagonals: T + 2 doubles per kind)
-    const unsigned ks = gs_table_stride(K, a.kstride);
-    constexpr unsigned RS = T + 2;
-    const unsigned tabsz = (unsigned)a.nkinds * ks + (K == 2 ? (unsigned)a.nkinds * RS : 0u);
-    double *rdiag = vtab + (size_t)a.nkinds * ks;  // K == 2 only: [nkinds][RS]
-    uint4 *ring = reinterpret_cast<uint4 *>(vtab + ((tabsz + 1u) & ~1u));  // [RING][recq][NGRP]
-    const unsigned pass_q = (unsigned)NGRP * a.recq;                        // uint4 per pass
+    const unsigned ks = gs_table_stride(a.kstride);
+    constexpr unsigned RS = T + 2;  // odd number of 16-byte pieces per kind
+    const unsigned ntab = GEN ? 0u : (unsigned)a.G * a.nkinds * ks;
+    double *rdiag = vtab + ((ntab + 1u) & ~1u);  // [nkinds][RS]
+    const unsigned nrd = GEN ? 0u : (unsigned)a.nkinds * RS;
+    uint4 *ring = reinterpret_cast<uint4 *>(rdiag + nrd);  // [RING][recq][NGRP]
+    const unsigned pass_q = (unsigned)NGRP * a.recq;        // uint4 per pass
     unsigned long long *mbar = reinterpret_cast<unsigned long long *>(ring + GS_RING * pass_q);
     double *fring = reinterpret_cast<double *>(mbar + GS_RING);  // [GS_FRING][NGRP][T]
 
@@ -151,29 +155,33 @@ __global__ void __launch_bounds__(NT, 1) k_gs_fused(const GsArgs a) {
     const bool valid = t < a.ld;
     const int woff = 2 * lane;
 
-    double2 c0 = make_double2(1.0, 1.0), c1 = make_double2(1.0, 1.0);
-    if (K == 2 && valid) {
-        c0 = ldg2(a.coef0 + t);
-        c1 = ldg2(a.coef1 + t);
+    unsigned g0 = 0, g1 = 0;  // groups of this lane's two time values
+    if (GROUPED && valid) {
+        g0 = (unsigned)__ldg(a.grp + t);
+        g1 = (unsigned)__ldg(a.grp + t + 1);
     }
+    double b0[NB], b1[NB];  // bulk kind: entry values for t and t + 1
+    double2 brd = make_double2(0.0, 0.0);
     if (!GEN) {
-        for (int k = threadIdx.x; k < a.nkinds * a.kstride; k += NT) {
-            const int kind = k / a.kstride;
-            vtab[kind * ks + (k - kind * a.kstride)] = __ldg(a.ktab + k);
+        for (int k = threadIdx.x; k < a.G * a.nkinds * a.kstride; k += NT) {
+            const int row = k / a.kstride;
+            vtab[row * ks + (k - row * a.kstride)] = __ldg(a.ktab + k);
         }
         __syncthreads();
-        if (K == 1) {
-            for (int k = threadIdx.x; k < a.nkinds; k += NT)
-                vtab[k * ks + a.maxnnz + 1] = 1.0 / vtab[k * ks + a.maxnnz];
-        } else {
-            for (int k = grp; k < a.nkinds; k += NGRP) {
-                const double e0 = vtab[k * ks + 2 * a.maxnnz];
-                const double e1 = vtab[k * ks + 2 * a.maxnnz + 1];
-                double2 r;
-                r.x = valid ? 1.0 / fma(c0.x, e0, c1.x * e1) : 0.0;
-                r.y = valid ? 1.0 / fma(c0.y, e0, c1.y * e1) : 0.0;
-                *reinterpret_cast<double2 *>(rdiag + k * RS + woff) = r;
+        for (int k = grp; k < a.nkinds; k += NGRP) {  // 1 / diagonal (entry 0)
+            double2 r;
+            r.x = valid ? 1.0 / vtab[(g0 * a.nkinds + k) * ks] : 0.0;
+            r.y = valid ? 1.0 / vtab[(g1 * a.nkinds + k) * ks] : 0.0;
+            *reinterpret_cast<double2 *>(rdiag + k * RS + woff) = r;
+        }
+        if (BULK) {
+#pragma unroll
+            for (int q = 0; q < NB; ++q) {
+                b0[q] = vtab[(g0 * a.nkinds + a.bulk_kind) * ks + q];
+                b1[q] = vtab[(g1 * a.nkinds + a.bulk_kind) * ks + q];
             }
+            brd.x = valid ? 1.0 / b0[0] : 0.0;
+            brd.y = valid ? 1.0 / b1[0] : 0.0;
         }
     }
     const int m0 = __ldg(a.item_step + item), m1 = __ldg(a.item_step + item + 1);
@@ -257,78 +265,60 @@ __global__ void __launch_bounds__(NT, 1) k_gs_fused(const GsArgs a) {
             const unsigned row = h.x & 0x7fffffffu;
             const bool store = (h.x >> 31) != 0u;
             const unsigned self = h.w & 0xffffu;
-            double2 s0 = make_double2(0.0, 0.0), s1 = make_double2(0.0, 0.0);
-            const double *kv = GEN ? nullptr : vtab + (unsigned)h.z * ks;
-            double2 uo = make_double2(0.0, 0.0);
+            double2 s = make_double2(0.0, 0.0), uo = make_double2(0.0, 0.0), rd;
             if (!GEN) {
                 // fixed trip count, entry 0 = the diagonal (u_i itself)
+                const bool bulk = BULK && (int)h.z == a.bulk_kind;
+                const double *kv0 = vtab + (g0 * a.nkinds + h.z) * ks;
+                const double *kv1 = GROUPED ? vtab + (g1 * a.nkinds + h.z) * ks : kv0;
 #pragma unroll
-                for (int q = 0; q < (NNZ ? NNZ : 8); ++q) {
-                    if (NNZ == 0 && q >= a.maxnnz) break;
-                    const unsigned sl = slot_of(nb, q);
+                for (int e = 0; e < (NNZ ? NNZ : 8); ++e) {
+                    if (NNZ == 0 && e >= a.maxnnz) break;
+                    const unsigned sl = slot_of(nb, e);
                     const double2 xv = *reinterpret_cast<const double2 *>(win + sl * T + woff);
-                    if (q == 0) uo = xv;
-                    if (K == 2) {
-                        const double2 av = *reinterpret_cast<const double2 *>(kv + 2 * q);
-                        s0.x = fma(av.x, xv.x, s0.x);
-                        s0.y = fma(av.x, xv.y, s0.y);
-                        s1.x = fma(av.y, xv.x, s1.x);
-                        s1.y = fma(av.y, xv.y, s1.y);
+                    if (e == 0) uo = xv;
+                    double a0, a1;
+                    if (bulk) {
+                        a0 = b0[BULK ? e : 0];
+                        a1 = b1[BULK ? e : 0];
                     } else {
-                        const double a0 = kv[q];
-                        s0.x = fma(a0, xv.x, s0.x);
-                        s0.y = fma(a0, xv.y, s0.y);
+                        a0 = kv0[e];
+                        a1 = GROUPED ? kv1[e] : a0;
                     }
+                    s.x = fma(a0, xv.x, s.x);
+                    s.y = fma(a1, xv.y, s.y);
                 }
+                rd = bulk ? brd
+                          : *reinterpret_cast<const double2 *>(rdiag + (unsigned)h.z * RS + woff);
             } else {
-                const size_t voff = (size_t)h.z;
+                const double *c0 = a.cvals + (size_t)g0 * a.vstride + h.z;
+                const double *c1 = a.cvals + (size_t)g1 * a.vstride + h.z;
+                rd.x = __ldg(c0);  // the diagonal: entry 0
+                rd.y = GROUPED ? __ldg(c1) : rd.x;
                 for (int base = 0; base < nnz; base += 8) {
                     if (base) nb = slot[NGRP * (1 + (base >> 3))];
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const int e = base + q;
+                    for (int qq = 0; qq < 8; ++qq) {
+                        const int e = base + qq;
                         if (e < nnz) {
-                            const unsigned sl = slot_of(nb, q);
+                            const unsigned sl = slot_of(nb, qq);
                             const double2 xv =
                                 *reinterpret_cast<const double2 *>(win + sl * T + woff);
-                            if (sl == self) uo = xv;  // the diagonal entry: u_i itself
-                            const double a0 = __ldg(a.v0 + voff + e);
-                            s0.x = fma(a0, xv.x, s0.x);
-                            s0.y = fma(a0, xv.y, s0.y);
-                            if (K == 2) {
-                                const double a1 = __ldg(a.v1 + voff + e);
-                                s1.x = fma(a1, xv.x, s1.x);
-                                s1.y = fma(a1, xv.y, s1.y);
-                            }
+                            if (e == 0) uo = xv;
+                            const double a0 = __ldg(c0 + e);
+                            s.x = fma(a0, xv.x, s.x);
+                            s.y = fma(GROUPED ? __ldg(c1 + e) : a0, xv.y, s.y);
                         }
                     }
                 }
             }
             double *up = win + self * T + woff;
             if (GEN) {
-                double2 dg;
-                if (K == 2) {
-                    s0.x = fma(c0.x, s0.x, c1.x * s1.x);
-                    s0.y = fma(c0.y, s0.y, c1.y * s1.y);
-                    const double e0 = __ldg(a.d0 + row), e1 = __ldg(a.d1 + row);
-                    dg.x = fma(c0.x, e0, c1.x * e1);
-                    dg.y = fma(c0.y, e0, c1.y * e1);
-                } else {
-                    dg.x = dg.y = __ldg(a.d0 + row);
-                }
-                uo.x += (fv.x - s0.x) / dg.x;
-                uo.y += (fv.y - s0.y) / dg.y;
-            } else if (K == 2) {
-                s0.x = fma(c0.x, s0.x, c1.x * s1.x);
-                s0.y = fma(c0.y, s0.y, c1.y * s1.y);
-                const double2 rd =
-                    *reinterpret_cast<const double2 *>(rdiag + (unsigned)h.z * RS + woff);
-                uo.x = fma(fv.x - s0.x, rd.x, uo.x);
-                uo.y = fma(fv.y - s0.y, rd.y, uo.y);
+                uo.x += (fv.x - s.x) / rd.x;
+                uo.y += (fv.y - s.y) / rd.y;
             } else {
-                const double rd = kv[a.maxnnz + 1];
-                uo.x = fma(fv.x - s0.x, rd, uo.x);
-                uo.y = fma(fv.y - s0.y, rd, uo.y);
+                uo.x = fma(fv.x - s.x, rd.x, uo.x);
+                uo.y = fma(fv.y - s.y, rd.y, uo.y);
             }
             *reinterpret_cast<double2 *>(up) = uo;
             if (store && valid) stv2(a.uout + (size_t)row * a.ld + tcol, uo);
@@ -356,9 +346,9 @@ struct stk_gs_prog {
     const uint4 *rec;
 };
 
-template <int LPO, int K, bool GEN, int NT, int NNZ>
+template <int LPO, bool GROUPED, bool GEN, int NT, int NNZ>
 static int launch_gs_fused(const GsArgs &a, int nitems, size_t smem, cudaStream_t s) {
-    auto kern = k_gs_fused<LPO, K, GEN, NT, NNZ>;
+    auto kern = k_gs_fused<LPO, GROUPED, GEN, NT, NNZ>;
     static thread_local size_t configured = 0;
     if (smem > configured) {
         STK_TRY(check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -372,17 +362,16 @@ static int launch_gs_fused(const GsArgs &a, int nitems, size_t smem, cudaStream_
 
 namespace stk {
 // shared with stk_mg.cu
-int gs_fused_run(const stk_gs_prog *pg, int K, int T, const double *ktab, int nkinds,
-                 const double *v0, const double *v1, const double *d0, const double *d1,
-                 const double *coef0, const double *coef1, const double *f, const double *uin,
-                 double *uout, int ld, cudaStream_t s) {
+int gs_fused_run(const stk_gs_prog *pg, int G, int T, const double *ktab, int nkinds,
+                 int bulk_kind, const double *cvals, size_t vstride, const int *grp,
+                 const double *f, const double *uin, double *uout, int ld, cudaStream_t s) {
     if (!pg) return fail(-1, "stk_gs_fused: null program");
-    if (K != 1 && K != 2) return fail(-1, "stk_gs_fused: K must be 1 or 2");
+    if (G < 1) return fail(-1, "stk_gs_fused: G must be >= 1");
     if (T != 8) return fail(-1, "stk_gs_fused: T must be 8");
     if (ld & 3) return fail(-1, "stk_gs_fused: pitch must be a multiple of 4");
     if (uin == uout) return fail(-1, "stk_gs_fused: u_in must not alias u_out");
-    if (K == 2 && (!coef0 || !coef1)) return fail(-1, "stk_gs_fused: K = 2 needs coefficients");
-    if (pg->generic ? (!v0 || !d0 || (K == 2 && (!v1 || !d1))) : (!ktab || nkinds < 1))
+    if (G > 1 && !grp) return fail(-1, "stk_gs_fused: several groups need the group table");
+    if (pg->generic ? !cvals : (!ktab || nkinds < 1))
         return fail(-1, "stk_gs_fused: matrix values missing");
     GsArgs a;
     a.item_step = pg->item_step;
@@ -392,36 +381,39 @@ int gs_fused_run(const stk_gs_prog *pg, int K, int T, const double *ktab, int nk
     a.recq = pg->recw / 4;
     a.lds = pg->ld;
     a.ktab = ktab;
+    a.G = G;
     a.nkinds = pg->generic ? 0 : nkinds;
     a.maxnnz = pg->maxnnz;
-    a.kstride = K * pg->maxnnz + 2;
+    a.kstride = pg->maxnnz + 2;
     a.nslots = pg->nslots;
-    a.v0 = v0;
-    a.v1 = v1;
-    a.d0 = d0;
-    a.d1 = d1;
-    a.coef0 = coef0;
-    a.coef1 = coef1;
+    a.bulk_kind = bulk_kind;
+    a.cvals = cvals;
+    a.vstride = vstride;
+    a.grp = grp;
     a.f = f;
     a.uin = uin;
     a.uout = uout;
     a.ld = ld;
     a.nchunks = (ld + T - 1) / T;
-    size_t tab = (size_t)a.nkinds * gs_table_stride(K, a.kstride) +
-                 (K == 2 ? (size_t)a.nkinds * (T + 2) : 0);
-    tab = (tab + 1) & ~(size_t)1;
+    size_t tab = 0;
+    if (!pg->generic) {
+        tab = (size_t)G * a.nkinds * gs_table_stride(a.kstride);
+        tab = ((tab + 1) & ~(size_t)1) + (size_t)a.nkinds * (T + 2);
+    }
     size_t smem = sizeof(double) * ((size_t)pg->nslots * T + tab) +
                   (size_t)GS_RING * pg->ngrp * pg->recw * 4 + GS_RING * 8 +
                   (size_t)GS_FRING * pg->ngrp * T * 8;
     if (smem > 227 * 1024) return fail(-1, "stk_gs_fused: window does not fit shared memory");
-#define STK_GSF(KK, GG, NN) launch_gs_fused<4, KK, GG, 512, NN>(a, pg->nitems, smem, s)
     if (pg->ngrp != 128)
         return fail(-1, "stk_gs_fused: program compiled for an unsupported group count");
-    if (pg->generic) return K == 1 ? STK_GSF(1, true, 0) : STK_GSF(2, true, 0);
+    const bool grouped = (grp != nullptr);
+#define STK_GSF(GG, GEN_, NN) launch_gs_fused<4, GG, GEN_, 512, NN>(a, pg->nitems, smem, s)
+    if (pg->generic) return grouped ? STK_GSF(true, true, 0) : STK_GSF(false, true, 0);
     if (pg->maxnnz > 8) return fail(-1, "stk_gs_fused: row kinds need <= 8 entries per row");
-    if (pg->maxnnz == 7) return K == 1 ? STK_GSF(1, false, 7) : STK_GSF(2, false, 7);
-    if (pg->maxnnz == 8) return K == 1 ? STK_GSF(1, false, 8) : STK_GSF(2, false, 8);
-    return K == 1 ? STK_GSF(1, false, 0) : STK_GSF(2, false, 0);
+    if (bulk_kind < 0 || bulk_kind >= nkinds) return fail(-1, "stk_gs_fused: bad bulk kind");
+    if (pg->maxnnz == 7) return grouped ? STK_GSF(true, false, 7) : STK_GSF(false, false, 7);
+    if (pg->maxnnz == 8) return grouped ? STK_GSF(true, false, 8) : STK_GSF(false, false, 8);
+    return grouped ? STK_GSF(true, false, 0) : STK_GSF(false, false, 0);
 #undef STK_GSF
 }
 }  // namespace stk
@@ -453,12 +445,11 @@ stk_gs_prog *stk_gs_prog_create(int nitems, int nslots, int maxnnz, int generic,
 
 void stk_gs_prog_destroy(stk_gs_prog *p) { delete p; }
 
-int stk_gs_fused(const stk_gs_prog *pg, int K, int T, const double *ktab, int nkinds,
-                 const double *v0, const double *v1, const double *d0, const double *d1,
-                 const double *coef0, const double *coef1, const double *f, const double *uin,
-                 double *uout, int ld, void *stream) {
-    return gs_fused_run(pg, K, T, ktab, nkinds, v0, v1, d0, d1, coef0, coef1, f, uin, uout, ld,
-                        as_stream(stream));
+int stk_gs_fused(const stk_gs_prog *pg, int G, int T, const double *ktab, int nkinds,
+                 int bulk_kind, const double *cvals, int64_t vstride, const int *group,
+                 const double *f, const double *uin, double *uout, int ld, void *stream) {
+    return gs_fused_run(pg, G, T, ktab, nkinds, bulk_kind, cvals, (size_t)vstride, group, f, uin,
+                        uout, ld, as_stream(stream));
 }
 
 // Host helper (HOST pointers): interval colouring of window lifetimes.  Row q

@@ -49,6 +49,45 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// The same with one matrix per GROUP of time slices on a shared pattern:
+// vals[g * vstride + p] is entry p of group g's matrix, grp[t] the group of
+// time slice t (multigrid levels of the C_j = MG(2^j M_x + alpha A_x) family,
+// heateq_mpi.py:143-153: every slice sees exactly the matrix the reference
+// forms for it).  A thread's two time values may belong to two groups.
+template <bool HAS_Z>
+__global__ void __launch_bounds__(256)
+    k_space_spmm_g(int nrows, const int *__restrict__ indptr, const int *__restrict__ indices,
+                   const double *__restrict__ vals, size_t vstride, const int *__restrict__ grp,
+                   const double *__restrict__ x, double alpha, double beta, const double *z,
+                   double *y, int ld, unsigned ld2) {
+    const unsigned total = (unsigned)nrows * ld2;
+    const unsigned stride = gridDim.x * 256u;
+    for (unsigned k = blockIdx.x * 256u + threadIdx.x; k < total; k += stride) {
+        unsigned i = k / ld2;
+        unsigned c = (k - i * ld2) * 2u;
+        const double *v0 = vals + (size_t)__ldg(grp + c) * vstride;
+        const double *v1 = vals + (size_t)__ldg(grp + c + 1) * vstride;
+        int p1 = __ldg(indptr + i + 1);
+        double2 s = make_double2(0.0, 0.0);
+        for (int p = __ldg(indptr + i); p < p1; ++p) {
+            double2 xv = ldv2(x + (size_t)__ldg(indices + p) * ld + c);
+            s.x = fma(__ldg(v0 + p), xv.x, s.x);
+            s.y = fma(__ldg(v1 + p), xv.y, s.y);
+        }
+        size_t o = (size_t)i * ld + c;
+        double2 out;
+        if (HAS_Z) {
+            double2 zv = ldv2(z + o);
+            out.x = fma(alpha, s.x, beta * zv.x);
+            out.y = fma(alpha, s.y, beta * zv.y);
+        } else {
+            out.x = alpha * s.x;
+            out.y = alpha * s.y;
+        }
+        stv2(y + o, out);
+    }
+}
+
 // One row of T against the time column of space dof i.
 __device__ __forceinline__ double time_row(int t, const int *__restrict__ indptr,
                                            const int *__restrict__ indices,
@@ -359,6 +398,27 @@ int launch_space_spmm(int nrows, const int *indptr, const int *indices, int K,
     }
 #undef STK_SPMM
     return check_launch("k_space_spmm");
+}
+
+int launch_space_spmm_grouped(int nrows, const int *indptr, const int *indices,
+                              const double *vals, size_t vstride, const int *grp, const double *x,
+                              double alpha, double beta, const double *z, double *y, int ld,
+                              cudaStream_t s) {
+    if (!grp)  // one group: the plain single-matrix kernel
+        return launch_space_spmm(nrows, indptr, indices, 1, vals, nullptr, nullptr, nullptr, x,
+                                 alpha, beta, z, y, ld, s);
+    if (nrows == 0) return 0;
+    unsigned ld2 = (unsigned)ld / 2u;
+    int64_t work = (int64_t)nrows * ld2;
+    if (work >= STK_MAX_ITEMS) return fail(-2, "stk_space_spmm: block too large for 32-bit grid");
+    if (beta != 0.0 && z == nullptr) return fail(-1, "stk_space_spmm: beta != 0 needs z");
+    if (beta != 0.0)
+        k_space_spmm_g<true><<<resident_grid(k_space_spmm_g<true>, 256, work), 256, 0, s>>>(
+            nrows, indptr, indices, vals, vstride, grp, x, alpha, beta, z, y, ld, ld2);
+    else
+        k_space_spmm_g<false><<<resident_grid(k_space_spmm_g<false>, 256, work), 256, 0, s>>>(
+            nrows, indptr, indices, vals, vstride, grp, x, alpha, beta, z, y, ld, ld2);
+    return check_launch("k_space_spmm_g");
 }
 
 }  // namespace stk

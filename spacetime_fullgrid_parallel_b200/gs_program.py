@@ -91,52 +91,76 @@ def graph_embedding(indptr, indices, n):
     return x, y
 
 
-def row_kinds(indptr, value_arrays, diag_arrays):
-    """Rows with bitwise identical value tuples (all base matrices, diagonal
-    included) share a *kind*: on a uniformly refined mesh a level has a
+def canonical_order(indptr, indices, value_arrays):
+    """Per row, the order in which a program lists the row's entries: the
+    diagonal first, then the off-diagonal entries sorted by their values in
+    the base matrices (ties: by column).  Rows of a uniformly refined mesh
+    whose stencils differ only by the numbering of the neighbours then carry
+    the same value sequence and share a *kind* (row_kinds).  Returns `canon`:
+    canon[indptr[i] + e] = CSR position of entry e of row i."""
+    n = len(indptr) - 1
+    nnz = np.diff(indptr).astype(np.int64)
+    rows = np.repeat(np.arange(n, dtype=np.int64), nnz)
+    cols = np.asarray(indices, dtype=np.int64)
+    keys = [cols]
+    for v in reversed(list(value_arrays)):
+        keys.append(np.asarray(v, dtype=np.float64))
+    keys.append(cols != rows)  # the diagonal entry first
+    keys.append(rows)
+    return np.lexsort(keys).astype(np.int64)
+
+
+def row_kinds(indptr, value_arrays, canon=None):
+    """Rows with bitwise identical value sequences (all arrays, in canonical
+    entry order) share a *kind*: on a uniformly refined mesh a level has a
     handful.  Returns (kind_of_row, representative_row_of_kind) or None if
     there are more than MAX_KINDS (unstructured mesh: generic path)."""
     n = len(indptr) - 1
     if n == 0:
         return None
     nnz = np.diff(indptr).astype(np.int64)
+    if (nnz == 0).any():
+        return None
+    if canon is None:
+        canon = np.arange(int(nnz.sum()), dtype=np.int64)
     rng = np.random.RandomState(12345)
     maxnnz = int(nnz.max())
     mult = rng.randint(1, 2**62, size=(len(value_arrays), maxnnz),
                        dtype=np.int64).astype(np.uint64) * np.uint64(2) + np.uint64(1)
     h = nnz.astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15)
-    rows = np.repeat(np.arange(n, dtype=np.int64), nnz)
-    within = np.arange(len(rows), dtype=np.int64) - np.repeat(
-        indptr[:-1].astype(np.int64), nnz)
     starts = indptr[:-1].astype(np.int64)
-    if (nnz == 0).any():
-        return None
+    within = np.arange(len(canon), dtype=np.int64) - np.repeat(starts, nnz)
+    vals = [np.ascontiguousarray(np.asarray(v, dtype=np.float64)[canon])
+            for v in value_arrays]
     with np.errstate(over='ignore'):
-        for k, v in enumerate(value_arrays):
-            bits = np.ascontiguousarray(v, dtype=np.float64).view(np.uint64)
-            contrib = bits * mult[k][within]
+        for k, v in enumerate(vals):
+            contrib = v.view(np.uint64) * mult[k][within]
             h += np.add.reduceat(contrib, starts) * np.uint64(k * 2 + 3)
-        for k, d in enumerate(diag_arrays):
-            bits = np.ascontiguousarray(d, dtype=np.float64).view(np.uint64)
-            h += bits * np.uint64(0xD6E8FEB86659FD93 + 2 * k)
     uniq, first, inv = np.unique(h, return_index=True, return_inverse=True)
     if len(uniq) > MAX_KINDS:
         return None
     # exact verification: every row equals its representative bit for bit
-    rep = first[inv]
-    if not np.array_equal(nnz, nnz[rep]):
+    if not kinds_hold(indptr, inv, first, vals):
         return None
-    rep_pos = indptr[:-1].astype(np.int64)[rep]
-    rep_pos = np.repeat(rep_pos, nnz) + within
-    for v in value_arrays:
+    return inv.astype(np.int32), first.astype(np.int64)
+
+
+def kinds_hold(indptr, kind_of_row, rep, canon_value_arrays):
+    """True if every row carries exactly (bit for bit) the value sequence of
+    its kind's representative row, for every array (already in canonical
+    entry order)."""
+    nnz = np.diff(indptr).astype(np.int64)
+    rep_row = np.asarray(rep)[np.asarray(kind_of_row)]
+    if not np.array_equal(nnz, nnz[rep_row]):
+        return False
+    starts = indptr[:-1].astype(np.int64)
+    within = np.arange(int(nnz.sum()), dtype=np.int64) - np.repeat(starts, nnz)
+    rep_pos = np.repeat(starts[rep_row], nnz) + within
+    for v in canon_value_arrays:
         v = np.ascontiguousarray(v, dtype=np.float64).view(np.uint64)
         if not np.array_equal(v, v[rep_pos]):
-            return None
-    for d in diag_arrays:
-        d = np.ascontiguousarray(d, dtype=np.float64).view(np.uint64)
-        if not np.array_equal(d, d[rep]):
-            return None
-    return inv.astype(np.int32), first.astype(np.int64)
+            return False
+    return True
 
 
 def _alloc_slots(start, end):
@@ -266,9 +290,9 @@ class GSProgram:
                     value is fetched while this op computes
                 [2] kind of the row, or the row's offset in the CSR arrays
                 [3] window slot | nnz << 16   (nnz = 0: padding, no-op)
-                [4:] uint16 window slot of every entry of the CSR row, in CSR
-                    order (generic programs) or diagonal first (programs with
-                    row kinds; unused entries name the row's own slot)
+                [4:] uint16 window slot of every entry of the row in the
+                    program's entry order (`canon`: the diagonal first);
+                    unused entries name the row's own slot
     loads:    ld[nloads, 2] int32 = (row, window slot)
     """
     def __init__(self):
@@ -323,7 +347,8 @@ def _tilings(embedding, per_col, S):
 
 def compile_program(indptr, indices, wave, nsweeps, backward, capacity,
                     embedding=None, kind_of_row=None, chunks=33, sms=148,
-                    max_redundancy=1.7, ngrp=128, tiling=None, verbose=False):
+                    max_redundancy=1.7, ngrp=128, tiling=None, canon=None,
+                    verbose=False):
     """Program for `nsweeps` sweeps (forward or backward) of the level whose
     sparsity pattern is (indptr, indices) and whose rows have wavefront numbers
     `wave`.  `capacity` = window slots available to a CTA, `ngrp` = row updates
@@ -345,10 +370,13 @@ def compile_program(indptr, indices, wave, nsweeps, backward, capacity,
     if nnz_row.max() > 64:
         return None
     rows_all = np.repeat(np.arange(n, dtype=np.int64), nnz_row)
-    isdiag = indices == rows_all
-    if np.count_nonzero(isdiag) != n:
+    if np.count_nonzero(indices == rows_all) != n:
         return None  # the kernel takes u_i from the row's diagonal entry
-    diag_pos = (np.nonzero(isdiag)[0] - indptr[:-1]).astype(np.int64)
+    if canon is None:  # diagonal first, then CSR order
+        canon = np.lexsort((indices, indices != rows_all, rows_all))
+    canon = np.asarray(canon, dtype=np.int64)
+    canon_cols = indices[canon]  # columns of the rows' entries, program order
+    assert np.array_equal(canon_cols[indptr[:-1]], np.arange(n))
     if embedding is None:
         embedding = graph_embedding(indptr, indices, n)
         if embedding is None:
@@ -473,7 +501,7 @@ def compile_program(indptr, indices, wave, nsweeps, backward, capacity,
         nop = len(grow)
         rnnz = nnz_row[grow].astype(np.int64)
         pos, seg = _expand(indptr, grow)
-        nb_slot = slot[np.searchsorted(region, indices[pos])]
+        nb_slot = slot[np.searchsorted(region, canon_cols[pos])]
         assert (nb_slot >= 0).all()
         tot = int(pass_loc[-1]) * ngrp
         rec = np.zeros((tot, recw), dtype=np.uint32)
@@ -487,14 +515,9 @@ def compile_program(indptr, indices, wave, nsweeps, backward, capacity,
         rec[dst, 3] = slot[r['op_row']].astype(np.uint32) | (rnnz.astype(np.uint32) << 16)
         slots16 = rec[:, 4:].view(np.uint16)  # (tot, 2 * (recw - 4))
         within = np.arange(len(pos), dtype=np.int64) - np.repeat(seg[:-1], rnnz)
-        if kind_of_row is not None:
-            # kinds: the diagonal entry first, then the others in CSR order
-            # (the kind tables are permuted the same way, diag_first()), and
-            # unused entries name the row's own slot (their table value is 0)
-            slots16[dst] = slot[r['op_row']].astype(np.uint16)[:, None]
-            dpos = np.repeat(diag_pos[grow], rnnz)
-            within = np.where(within == dpos, 0,
-                              np.where(within < dpos, within + 1, within))
+        # entries in the program's (canonical) order, the diagonal first; unused
+        # entries name the row's own slot (their table value is 0)
+        slots16[dst] = slot[r['op_row']].astype(np.uint16)[:, None]
         slots16[np.repeat(dst, rnnz), within] = nb_slot.astype(np.uint16)
         # f prefetch hint: the row of the record PREFETCH passes later
         ahead = np.arange(tot, dtype=np.int64) + PREFETCH * ngrp
@@ -528,6 +551,7 @@ def compile_program(indptr, indices, wave, nsweeps, backward, capacity,
     prog.maxnnz, prog.recw, prog.ngrp = maxnnz, recw, ngrp
     prog.generic = kind_of_row is None
     prog.tiling = tiling
+    prog.canon = canon
     prog.stats = {
         'rows': n, 'items': len(sched), 'stages': S,
         'columns': ncols, 'ops': int(nops), 'redundancy': redundancy,
@@ -542,16 +566,6 @@ def compile_program(indptr, indices, wave, nsweeps, backward, capacity,
         'bytes': int(prog.op.nbytes + prog.ld.nbytes + prog.step_info.nbytes),
     }
     return prog
-
-
-def diag_first(indptr, indices, row):
-    """Positions of row `row`'s CSR entries in the order the records of a
-    program with row kinds list them: the diagonal entry, then the others."""
-    p0, p1 = int(indptr[row]), int(indptr[row + 1])
-    cols = np.asarray(indices[p0:p1])
-    d = int(np.nonzero(cols == row)[0][0])
-    return np.array([p0 + d] + [p for p in range(p0, p1) if p != p0 + d],
-                    dtype=np.int64)
 
 
 def wavefronts(indptr, indices):

@@ -32,6 +32,7 @@ FUSED_T = int(os.environ.get('STK_GS_T', '8'))
 FUSED_SMEM = 224 * 1024
 FUSED_MIN_ROWS = int(os.environ.get('STK_GS_FUSED_MIN_ROWS', '256'))
 FUSED_NGRP = int(os.environ.get('STK_GS_NGRP', '128'))  # 512 threads / 4 lanes
+MAX_GROUPS = 16  # value tables the fused kernel keeps in shared memory
 
 
 def fused_enabled():
@@ -47,31 +48,36 @@ def _dev_bytes(a, device, keep):
 
 
 class FusedLevel:
-    """Device-resident programs of one level: nu forward and nu backward
-    sweeps, plus the row kinds that index a handle's value table."""
-    def __init__(self, indptr, indices, wave, nsweeps, value_arrays,
-                 diag_arrays, device, chunks=33, sms=148, T=None,
-                 generic=False, capacity=None, ngrp=None):
+    """Device-resident programs of one level (nu forward and nu backward
+    sweeps), compiled once from the pattern and the BASE matrices' values; any
+    set of group matrices on that pattern can run them (`values_for`)."""
+    def __init__(self, indptr, indices, wave, nsweeps, base_values, device,
+                 chunks=33, sms=148, T=None, generic=False, capacity=None,
+                 ngrp=None):
         self.ok = False
         self.handles = []
         self._keep = []
         self.T = T = FUSED_T if T is None else T
+        self.indptr = np.asarray(indptr, dtype=np.int64)
         self.maxnnz = int(np.diff(indptr).max())
+        self.canon = gs_program.canonical_order(indptr, indices, base_values)
         # the kernel's branch-free row product holds <= 8 entries per row
         kinds = None if generic or self.maxnnz > 8 else gs_program.row_kinds(
-            indptr, value_arrays, diag_arrays)
+            indptr, base_values, self.canon)
         if kinds is None:
             self.kind_of_row, self.rep = None, None
-            self.nkinds, tab_bytes = 0, 0
+            self.nkinds, self.bulk_kind, tab_bytes = 0, -1, 0
         else:
             self.kind_of_row, self.rep = kinds
             self.nkinds = len(self.rep)
-            # the widest table any handle on this pattern may need (K = 2)
-            tab_bytes = 8 * self.nkinds * (2 * self.maxnnz + 4 + T + 2) + 16
+            self.bulk_kind = int(np.argmax(np.bincount(self.kind_of_row)))
+            # room for the value tables of up to MAX_GROUPS groups
+            tab_bytes = 8 * self.nkinds * (MAX_GROUPS * (self.maxnnz + 3) + T
+                                           + 2) + 16
         ngrp = FUSED_NGRP if ngrp is None else ngrp
         if capacity is None:
-            # what the window may take: shared memory minus the value tables
-            # and the record ring (csrc/stk_gsfused.cu: GS_RING pass slots)
+            # what the window may take: shared memory minus the value tables,
+            # the record ring and the f ring (csrc/stk_gsfused.cu)
             recw = 8 + 4 * max(0, (self.maxnnz - 8 + 7) // 8)
             rings = 8 * ngrp * recw * 4 + 64 + gs_program.PREFETCH * ngrp * T * 8
             capacity = min(65535, (FUSED_SMEM - tab_bytes - rings) // (8 * T))
@@ -85,7 +91,7 @@ class FusedLevel:
         for backward in (False, True):
             pg = gs_program.compile_program(
                 indptr, indices, wave, nsweeps, backward, capacity,
-                embedding=emb, kind_of_row=self.kind_of_row,
+                embedding=emb, kind_of_row=self.kind_of_row, canon=self.canon,
                 chunks=chunks, sms=sms, ngrp=ngrp,
                 tiling=progs[0].tiling if progs else None)
             if pg is None:
@@ -101,44 +107,52 @@ class FusedLevel:
                 pg.ngrp, *[ptr(t) for t in d]))
             assert h.value, 'stk_gs_prog_create failed'
             self.handles.append(h)
-        self.indptr = np.asarray(indptr, dtype=np.int64)
-        self.indices = np.asarray(indices, dtype=np.int64)
         self.device = device
         self.ok = True
 
-    def kind_table(self, value_arrays, diag_arrays):
-        """Device table [nkinds][K * maxnnz + 2] of a handle's values
-        (include/stk.h, stk_gs_fused), or None for generic programs."""
-        if self.rep is None:
+    def values_for(self, group_values):
+        """Device arrays that let the programs run with these G matrices
+        (CSR-order value arrays on the level's pattern): (ktab, cvals), one of
+        them None, or None if the programs cannot (they were compiled with row
+        kinds and some group's values differ inside a kind)."""
+        G = len(group_values)
+        canon_vals = [np.ascontiguousarray(np.asarray(v)[self.canon])
+                      for v in group_values]
+        if self.rep is None:  # generic programs: values at the CSR offsets
+            t = torch.from_numpy(np.stack(canon_vals)).to(self.device)
+            return None, t
+        if G > MAX_GROUPS or not gs_program.kinds_hold(
+                self.indptr, self.kind_of_row, self.rep, canon_vals):
             return None
-        K = len(value_arrays)
-        tab = np.zeros((self.nkinds, K * self.maxnnz + 2))
+        tab = np.zeros((G, self.nkinds, self.maxnnz + 2))
         for k, r in enumerate(self.rep):
-            # the order of the program's records: diagonal entry first
-            order = gs_program.diag_first(self.indptr, self.indices, r)
-            for j, v in enumerate(value_arrays):
-                tab[k, j:K * len(order):K] = np.asarray(v)[order]
-            for j, d in enumerate(diag_arrays):
-                tab[k, K * self.maxnnz + j] = d[r]
-        t = torch.from_numpy(tab).to(self.device)
-        self._keep.append(t)
-        return t
+            p0, p1 = self.indptr[r], self.indptr[r + 1]
+            for g, v in enumerate(canon_vals):
+                tab[g, k, :p1 - p0] = v[p0:p1]
+        return torch.from_numpy(tab).to(self.device), None
 
-    def sweeps(self, backward, K, tab, vals, diags, coefs, f, u_in, u_out):
-        """u_out <- the level's nu sweeps (device blocks); tests/microbench."""
-        v = [ptr(x) for x in vals] + [None] * (2 - len(vals))
-        d = [ptr(x) for x in diags] + [None] * (2 - len(diags))
-        c = [ptr(x) for x in coefs] + [None] * (2 - len(coefs))
-        check(lib().stk_gs_fused(self.handles[int(bool(backward))], K, self.T,
-                                 ptr(tab), self.nkinds, v[0], v[1], d[0], d[1],
-                                 c[0], c[1], ptr(f), ptr(u_in), ptr(u_out),
-                                 f.shape[1], stream()))
+    def sweeps(self, backward, vals, grp, f, u_in, u_out):
+        """u_out <- the level's nu sweeps (device blocks) with the matrices
+        `vals` = values_for(...); tests / microbench."""
+        ktab, cvals = vals
+        G = (ktab if ktab is not None else cvals).shape[0]
+        check(lib().stk_gs_fused(self.handles[int(bool(backward))], G, self.T,
+                                 ptr(ktab), self.nkinds, self.bulk_kind,
+                                 ptr(cvals), int(self.indptr[-1]), ptr(grp),
+                                 ptr(f), ptr(u_in), ptr(u_out), f.shape[1],
+                                 stream()))
 
-    def attach(self, mg_handle, level, value_arrays, diag_arrays):
-        tab = self.kind_table(value_arrays, diag_arrays)
+    def attach(self, mg_handle, level, group_values, keep):
+        """Returns False if these values cannot use the programs."""
+        vals = self.values_for(group_values)
+        if vals is None:
+            return False
+        keep.extend(t for t in vals if t is not None)
         check(lib().stk_mg_set_fused(mg_handle, level, self.handles[0],
-                                     self.handles[1], ptr(tab), self.nkinds,
+                                     self.handles[1], ptr(vals[0]),
+                                     self.nkinds, self.bulk_kind, ptr(vals[1]),
                                      self.T))
+        return True
 
     def __del__(self):
         try:
@@ -149,10 +163,14 @@ class FusedLevel:
             pass
 
 
-def _project(pattern_keys, mat, ncols):
+def _project(pattern_keys, mat, ncols, pattern=None):
     """Values of `mat` laid out on the (sorted) union pattern."""
     mat = sp.csr_matrix(mat)
     mat.sort_indices()
+    if (pattern is not None and mat.nnz == pattern.nnz
+            and np.array_equal(mat.indptr, pattern.indptr)
+            and np.array_equal(mat.indices, pattern.indices)):
+        return mat.data.astype(np.float64)
     rows = np.repeat(np.arange(mat.shape[0], dtype=np.int64),
                      np.diff(mat.indptr))
     keys = rows * ncols + mat.indices
@@ -191,27 +209,24 @@ def gauss_seidel_schedule(indptr, indices, return_wave=False):
 
 
 class MGContext:
-    """Per-slice coefficients of a block with pitch ld (device arrays)."""
+    """The groups of a block with pitch ld: slices with equal coefficients
+    share a group; device arrays for the kernels, the handle that holds the
+    groups' hierarchies."""
     def __init__(self, family, coefs_per_slice, ld):
         n = len(coefs_per_slice)
         assert 1 <= n <= ld
-        dev = family.device
-        K = family.K
         distinct = []
         group = np.zeros(ld, dtype=np.int32)
-        table = np.zeros((K, ld))
         for t in range(ld):
             c = tuple(float(v) for v in coefs_per_slice[min(t, n - 1)])
-            assert len(c) == K
+            assert len(c) == family.K
             if c not in distinct:
                 distinct.append(c)
             group[t] = distinct.index(c)
-            table[:, t] = c
-        inv = np.stack([family.coarse_inverse(c) for c in distinct])
-        self.coef = [torch.from_numpy(table[k].copy()).to(dev)
-                     for k in range(K)]
-        self.inv = torch.from_numpy(np.ascontiguousarray(inv)).to(dev)
-        self.group = torch.from_numpy(group).to(dev)
+        self.groups = tuple(distinct)
+        self.handle, self.inv = family.handle_for(self.groups)
+        self.group = (torch.from_numpy(group).to(family.device)
+                      if len(distinct) > 1 else None)
         self.ld = ld
 
 
@@ -229,23 +244,21 @@ def _workspace(device, doubles):
 
 class MultiGridFamily:
     """All V-cycle preconditioners MG(sum_k c_k base_mats[k]) on one mesh
-    hierarchy, K = len(base_mats) in {1, 2}."""
+    hierarchy.  Pattern, Gauss-Seidel schedule, transfer operators and the
+    fused smoother programs are built once; a set of coefficient tuples (the
+    GROUPS of a block's time slices) gets a handle whose level matrices are the
+    Galerkin products of each combined matrix, formed exactly as the reference
+    forms them (heateq_mpi.py:97-98,143-153; multigrid.py:140-145)."""
     def __init__(self, base_mats, hierarchy, smoothsteps=2, vcycles=1,
                  device=None, ld_hint=None):
         self.K = K = len(base_mats)
-        assert K in (1, 2)
+        assert K >= 1
+        self.base_mats = [sp.csr_matrix(B, dtype=np.float64) for B in base_mats]
         self.hierarchy = hierarchy
         self.smoothsteps, self.vcycles = smoothsteps, vcycles
         self.device = dev = _device() if device is None else device
-        J = hierarchy.J
-        # Galerkin hierarchies, coarse from fine (multigrid.py:140-145)
-        mats = []
-        for B in base_mats:
-            lv = [sp.csr_matrix(B, dtype=np.float64)]
-            for j in reversed(range(J)):
-                lv.insert(0, (hierarchy.R_mats[j] @ lv[0]
-                              @ hierarchy.P_mats[j]).tocsr())
-            mats.append(lv)
+        self.J = J = hierarchy.J
+        mats = [self._galerkin(B) for B in self.base_mats]
         self.level_mats = mats
         self.shape = mats[0][-1].shape
         n0 = mats[0][0].shape[0]
@@ -253,15 +266,11 @@ class MultiGridFamily:
             raise ValueError('coarsest level has %d dofs (> %d): the dense '
                              'coarse solve needs a coarser mesh' %
                              (n0, MAX_COARSE))
-        self._inv_cache = {}
         self._ctx_cache = {}
-        self._keep = []  # device tensors referenced by the C handle
-        self.handle = ctypes.c_void_p(
-            lib().stk_mg_create(J + 1, smoothsteps, vcycles, K))
-        assert self.handle.value, 'stk_mg_create failed'
+        self._handles = {}  # groups -> (handle, inverses, kept tensors)
+        self._keep = []  # device tensors shared by the handles
         self.num_phases = []
-        self._levels = []  # per level: host values/diagonals + shared device arrays
-        self._uniform = {}  # coefs -> single-matrix handle
+        self._levels = []
 
         def up(a, dt):
             t = torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(dev)
@@ -280,115 +289,95 @@ class MultiGridFamily:
             pat.sort_indices()
             rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(pat.indptr))
             keys = rows * n + pat.indices
-            vals = [_project(keys, mats[k][l], n) for k in range(K)]
-            diags = [mats[k][l].diagonal() for k in range(K)]
+            base_vals = [_project(keys, mats[k][l], n, pat) for k in range(K)]
             order, phase_ptr, wave = gauss_seidel_schedule(
                 pat.indptr, pat.indices, return_wave=True)
             self.num_phases.append(len(phase_ptr) - 1)
-            d_indptr, d_indices = up(pat.indptr, np.int32), up(
-                pat.indices, np.int32)
-            d_vals = [up(v, np.float64) for v in vals]
-            d_diag = [up(d, np.float64) for d in diags]
-            d_order = up(order, np.int32)
-            check(lib().stk_mg_set_level(
-                self.handle, l, n, ptr(d_indptr), ptr(d_indices),
-                ptr(d_vals[0]), ptr(d_vals[1]) if K == 2 else None,
-                ptr(d_diag[0]), ptr(d_diag[1]) if K == 2 else None,
-                ptr(d_order), phase_ptr.ctypes.data, len(phase_ptr) - 1))
             fused = None
             if (l >= 1 and fused_enabled() and smoothsteps > 0
                     and n >= FUSED_MIN_ROWS and len(phase_ptr) - 1 <= 8):
                 chunks = -(-(ld_hint or 256) // FUSED_T)
                 fused = FusedLevel(pat.indptr, pat.indices, wave, smoothsteps,
-                                   vals, diags, dev,
-                                   chunks=chunks,
+                                   base_vals, dev, chunks=chunks,
                                    sms=torch.cuda.get_device_properties(
                                        dev).multi_processor_count)
-                if fused.ok:
-                    fused.attach(self.handle, l, vals, diags)
-                else:
+                if not fused.ok:
                     fused = None
-            self._levels.append({
-                'n': n, 'vals': vals, 'diags': diags, 'indptr': d_indptr,
-                'indices': d_indices, 'order': d_order, 'phase_ptr': phase_ptr,
-                'transfer': None, 'fused': fused
-            })
+            lv = {'n': n, 'nnz': int(pat.nnz), 'pattern': pat, 'keys': keys,
+                  'indptr': up(pat.indptr, np.int32),
+                  'indices': up(pat.indices, np.int32),
+                  'order': up(order, np.int32), 'phase_ptr': phase_ptr,
+                  'transfer': None, 'fused': fused}
             if l >= 1:
                 P = sp.csr_matrix(hierarchy.P_mats[l - 1], dtype=np.float64)
                 R = sp.csr_matrix(hierarchy.R_mats[l - 1], dtype=np.float64)
                 P.sort_indices()
                 R.sort_indices()
-                tp = [up(P.indptr, np.int32), up(P.indices, np.int32),
-                      up(P.data, np.float64), up(R.indptr, np.int32),
-                      up(R.indices, np.int32), up(R.data, np.float64)]
-                check(lib().stk_mg_set_transfer(self.handle, l,
-                                                *[ptr(t) for t in tp]))
-                self._levels[-1]['transfer'] = tp
+                lv['transfer'] = [up(P.indptr, np.int32), up(P.indices, np.int32),
+                                  up(P.data, np.float64), up(R.indptr, np.int32),
+                                  up(R.indices, np.int32), up(R.data, np.float64)]
+            self._levels.append(lv)
+
+    def _galerkin(self, mat):
+        """Level matrices, coarse from fine (multigrid.py:140-145)."""
+        lv = [sp.csr_matrix(mat, dtype=np.float64)]
+        for j in reversed(range(self.J)):
+            lv.insert(0, (self.hierarchy.R_mats[j] @ lv[0]
+                          @ self.hierarchy.P_mats[j]).tocsr())
+        return lv
+
+    def combined(self, coefs):
+        """sum_k coefs[k] * base_mats[k], the expression of heateq_mpi.py:97-98."""
+        mat = coefs[0] * self.base_mats[0]
+        for c, B in zip(coefs[1:], self.base_mats[1:]):
+            mat = mat + c * B
+        return sp.csr_matrix(mat)
 
     def __del__(self):
         try:
-            for h, _ in list(getattr(self, '_uniform', {}).values()):
+            for h, _inv, _keep in list(getattr(self, '_handles', {}).values()):
                 lib().stk_mg_destroy(h)
-            self._uniform = {}
-            if self.handle and self.handle.value:
-                lib().stk_mg_destroy(self.handle)
-                self.handle = None
+            self._handles = {}
         except Exception:
             pass
 
-    def uniform_handle(self, coefs):
-        """Single-matrix (K = 1) hierarchy of sum_k coefs[k] * base_mats[k] for
-        blocks whose slices all share the coefficients (K_x in S): the level
-        values are combined once on the host -- which is what the reference
-        does (heateq_mpi.py:97-98) -- so the kernels read one value array and
-        no per-slice coefficients.  Pattern, schedule and transfer operators
-        are shared with the family."""
-        coefs = tuple(float(c) for c in coefs)
-        if coefs not in self._uniform:
+    def handle_for(self, groups):
+        """(stk_mg handle, device coarse inverses) for a tuple of coefficient
+        tuples; built on first use."""
+        groups = tuple(tuple(float(c) for c in g) for g in groups)
+        if groups not in self._handles:
+            G = len(groups)
+            chains = [self._galerkin(self.combined(g)) for g in groups]
             h = ctypes.c_void_p(lib().stk_mg_create(
-                len(self._levels), self.smoothsteps, self.vcycles, 1))
+                len(self._levels), self.smoothsteps, self.vcycles, G))
             assert h.value, 'stk_mg_create failed'
             keep = []
             for l, lv in enumerate(self._levels):
-                vals = sum(c * v for c, v in zip(coefs, lv['vals']))
-                diag = sum(c * d for c, d in zip(coefs, lv['diags']))
-                dv = torch.from_numpy(np.ascontiguousarray(vals)).to(self.device)
-                dd = torch.from_numpy(np.ascontiguousarray(diag)).to(self.device)
+                vals = [_project(lv['keys'], ch[l], lv['n'], lv['pattern'])
+                        for ch in chains]
+                diag = [ch[l].diagonal() for ch in chains]
+                dv = torch.from_numpy(np.stack(vals)).to(self.device)
+                dd = torch.from_numpy(np.stack(diag)).to(self.device)
                 keep += [dv, dd]
                 check(lib().stk_mg_set_level(
-                    h, l, lv['n'], ptr(lv['indptr']), ptr(lv['indices']),
-                    ptr(dv), None, ptr(dd), None, ptr(lv['order']),
+                    h, l, lv['n'], lv['nnz'], ptr(lv['indptr']),
+                    ptr(lv['indices']), ptr(dv), ptr(dd), ptr(lv['order']),
                     lv['phase_ptr'].ctypes.data, len(lv['phase_ptr']) - 1))
                 if lv['transfer'] is not None:
                     check(lib().stk_mg_set_transfer(
                         h, l, *[ptr(t) for t in lv['transfer']]))
                 if lv['fused'] is not None:
-                    lv['fused'].attach(h, l, [vals], [diag])
-            inv = torch.from_numpy(np.ascontiguousarray(
-                self.coarse_inverse(coefs))).to(self.device)
-            keep.append(inv)
-            self._uniform[coefs] = (h, keep)
-        return self._uniform[coefs]
-
-    def apply_uniform(self, coefs, b, x):
-        """x <- MG(sum_k coefs[k] B_k) b, the same matrix for every slice."""
-        if self.K == 1:
-            return self.apply_block(b, x, self.context([coefs], b.shape[1]))
-        h, keep = self.uniform_handle(coefs)
-        ld = b.shape[1]
-        ws = _workspace(b.device, lib().stk_mg_workspace(h, ld))
-        check(lib().stk_mg_apply(h, None, None, ptr(keep[-1]), None, ptr(b),
-                                 ptr(x), ld, ptr(ws), stream()))
+                    lv['fused'].attach(h, l, vals, keep)
+            # coarsest level: exact inverse (the reference factorises it with
+            # SuperLU, multigrid.py:161-165; it is 1x1 for `square`)
+            inv = np.stack([np.linalg.inv(ch[0].toarray()) for ch in chains])
+            dinv = torch.from_numpy(np.ascontiguousarray(inv)).to(self.device)
+            self._handles[groups] = (h, dinv, keep)
+        h, dinv, _ = self._handles[groups]
+        return h, dinv
 
     def coarse_inverse(self, coefs):
-        """Dense inverse of the coarsest matrix (the reference factorises it
-        with SuperLU, multigrid.py:161-165; it is 1x1 for `square`)."""
-        coefs = tuple(float(c) for c in coefs)
-        if coefs not in self._inv_cache:
-            A0 = sum(c * self.level_mats[k][0].toarray()
-                     for k, c in enumerate(coefs))
-            self._inv_cache[coefs] = np.linalg.inv(A0)
-        return self._inv_cache[coefs]
+        return np.linalg.inv(self._galerkin(self.combined(coefs))[0].toarray())
 
     def context(self, coefs_per_slice, ld):
         key = (tuple(tuple(float(v) for v in c) for c in coefs_per_slice), ld)
@@ -396,16 +385,17 @@ class MultiGridFamily:
             self._ctx_cache[key] = MGContext(self, coefs_per_slice, ld)
         return self._ctx_cache[key]
 
+    def apply_uniform(self, coefs, b, x):
+        """x <- MG(sum_k coefs[k] B_k) b, the same matrix for every slice."""
+        return self.apply_block(b, x, self.context([coefs], b.shape[1]))
+
     def apply_block(self, b, x, ctx):
-        """x <- MG(A(t)) b for every slice t of the block."""
+        """x <- MG(A_{group(t)}) b for every slice t of the block."""
         ld = b.shape[1]
         assert ctx.ld == ld and b.shape[0] == self.shape[0]
-        ws = _workspace(b.device, lib().stk_mg_workspace(self.handle, ld))
-        c0 = ptr(ctx.coef[0]) if self.K == 2 else None
-        c1 = ptr(ctx.coef[1]) if self.K == 2 else None
-        check(lib().stk_mg_apply(self.handle, c0, c1, ptr(ctx.inv),
-                                 ptr(ctx.group), ptr(b), ptr(x), ld, ptr(ws),
-                                 stream()))
+        ws = _workspace(b.device, lib().stk_mg_workspace(ctx.handle, ld))
+        check(lib().stk_mg_apply(ctx.handle, ptr(ctx.group), ptr(ctx.inv),
+                                 ptr(b), ptr(x), ld, ptr(ws), stream()))
 
     def member(self, coefs):
         """The MultiGrid operator of sum_k coefs[k] * base_mats[k]."""
@@ -433,9 +423,9 @@ class Smoother:
         ]
         self.handle = ctypes.c_void_p(lib().stk_mg_create(2, its, 1, 1))
         ip, ix, dv, dd, od = self._keep
-        check(lib().stk_mg_set_level(self.handle, 1, self.n, ptr(ip), ptr(ix),
-                                     ptr(dv), None, ptr(dd), None, ptr(od),
-                                     phase_ptr.ctypes.data,
+        check(lib().stk_mg_set_level(self.handle, 1, self.n, int(mat.nnz),
+                                     ptr(ip), ptr(ix), ptr(dv), ptr(dd),
+                                     ptr(od), phase_ptr.ctypes.data,
                                      len(phase_ptr) - 1))
 
     def __del__(self):
@@ -457,9 +447,8 @@ class Smoother:
         df = torch.zeros((self.n, ld), dtype=torch.float64, device=dev)
         du[:, :k] = torch.from_numpy(np.ascontiguousarray(u2)).to(dev)
         df[:, :k] = torch.from_numpy(np.ascontiguousarray(f2)).to(dev)
-        check(lib().stk_mg_smooth(self.handle, 1, self.its,
-                                  int(backward), None, None, ptr(df), ptr(du),
-                                  ld, stream()))
+        check(lib().stk_mg_smooth(self.handle, 1, self.its, int(backward),
+                                  None, ptr(df), ptr(du), ld, stream()))
         u[...] = du[:, :k].cpu().numpy().reshape(np.shape(u))
 
     def PreSmooth(self, u, f):
@@ -490,11 +479,7 @@ class MultiGrid:
     @property
     def mats(self):
         """Level matrices, coarse to fine (multigrid.py:140-154)."""
-        lm = self.family.level_mats
-        return [
-            sum(c * lm[k][l] for k, c in enumerate(self.coefs))
-            for l in range(len(lm[0]))
-        ]
+        return self.family._galerkin(self.family.combined(self.coefs))
 
     def apply_block(self, x, out, ctx=None):
         if ctx is None:

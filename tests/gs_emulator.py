@@ -8,12 +8,12 @@ store flag write the global result.  Used by the CPU tests to check the
 compiler against the sequential sweep of oracle/gs.c."""
 import numpy as np
 
-from spacetime_fullgrid_parallel_b200.gs_program import (LOOKAHEAD, PREFETCH,
-                                                         diag_first)
+from spacetime_fullgrid_parallel_b200.gs_program import LOOKAHEAD, PREFETCH
 
 
 def emulate(prog, indptr, data, diag, f, u_in, check_hazards=True,
             indices=None):
+    data = np.asarray(data)[prog.canon]  # the program's entry order
     """u_out (n, k) after the program's sweeps; f, u_in: (n, k) (u_in None =
     zero guess); data: CSR values on the program's pattern."""
     n, k = f.shape
@@ -60,10 +60,9 @@ def emulate(prog, indptr, data, diag, f, u_in, check_hazards=True,
                     vals = data[indptr[i]:indptr[i + 1]]
                     if prog.generic:
                         assert int(o[q, 2]) == indptr[i]
-                    else:  # diagonal first; unused entries = own slot
-                        vals = data[diag_first(indptr, indices, i)]
-                        assert sl[0] == self_slot[q]
-                        assert (slots16[q, nnz[q]:] == self_slot[q]).all()
+                    # the diagonal entry first; unused entries = own slot
+                    assert sl[0] == self_slot[q]
+                    assert (slots16[q, nnz[q]:] == self_slot[q]).all()
                     ax = vals @ win[sl]
                     new[q] = win[self_slot[q]] + (f[i] - ax) / diag[i]
                 assert not np.isnan(new).any(), 'op read an invalid window slot'

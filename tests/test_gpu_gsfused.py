@@ -43,15 +43,13 @@ def _oracle(pat, vals, f, u0, nsw, backward):
     return u.T
 
 
-@pytest.mark.parametrize('ngrp', [128])
 @pytest.mark.parametrize('generic', [False, True])
 @pytest.mark.parametrize('Js,capacity', [(4, None), (6, 1500), (6, None)])
-def test_fused_sweeps_match_sequential(cuda, Js, capacity, generic, ngrp):
+def test_fused_sweeps_match_sequential(cuda, Js, capacity, generic):
     import torch
     from spacetime_fullgrid_parallel_b200 import gs_program
     from spacetime_fullgrid_parallel_b200.multigrid import FusedLevel
     from spacetime_fullgrid_parallel_b200.mpi_vector import pitch
-    T = 8
     pat, vals, diags = _level(Js)
     n = pat.shape[0]
     wave, depth = gs_program.wavefronts(pat.indptr, pat.indices)
@@ -61,49 +59,45 @@ def test_fused_sweeps_match_sequential(cuda, Js, capacity, generic, ngrp):
     rng = np.random.RandomState(5)
     F = rng.rand(n, nt)
     U0 = rng.rand(n, nt)
-    coef = np.stack([2.0**rng.randint(0, 6, size=nt), np.full(nt, 0.3)])
+    # every slice has its own matrix c0(t) M + c1 A: 6 groups, interleaved
+    c0 = 2.0**rng.randint(0, 6, size=nt)
+    groups = sorted(set(c0))
+    gvals = [c * vals[0] + 0.3 * vals[1] for c in groups]
+    grp = np.array([groups.index(c) for c in c0] + [groups.index(c0[-1])] *
+                   (ld - nt), dtype=np.int32)
 
     def dev(a):
         t = torch.zeros((n, ld), dtype=torch.float64, device=cuda)
         t[:, :nt] = torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
         return t
 
-    def dvec(a, length=None):
-        a = np.asarray(a, dtype=np.float64)
-        if length is not None:  # per-slice table, last value repeated on pads
-            a = np.concatenate([a, np.full(length - len(a), a[-1])])
-        return torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
-
     for nsw in (3, 1):
-        fl = FusedLevel(pat.indptr, pat.indices, wave, nsw, vals, diags, cuda,
-                        chunks=1, sms=3, generic=generic, capacity=capacity,
-                        ngrp=ngrp)
+        fl = FusedLevel(pat.indptr, pat.indices, wave, nsw, vals, cuda,
+                        chunks=1, sms=3, generic=generic, capacity=capacity)
         assert fl.ok, 'program did not compile'
+        if not generic:  # entries sorted by value: one kind covers the interior
+            assert np.bincount(fl.kind_of_row)[fl.bulk_kind] > 0.8 * n
         if capacity is not None:
             assert fl.programs[0].nitems > 1
         f_d, u_d = dev(F), dev(U0)
-        # K = 2: per-slice matrices c0(t) M + c1(t) A
-        tab2 = fl.kind_table(vals, diags)
-        dv, dd = [dvec(v) for v in vals], [dvec(d) for d in diags]
-        dc = [dvec(coef[0], ld), dvec(coef[1], ld)]
+        dvals = fl.values_for(gvals)
+        assert dvals is not None
+        dgrp = torch.from_numpy(grp).to(cuda)
         for backward in (False, True):
             for zero in (True, False):
                 out = torch.full((n, ld), 7.0, dtype=torch.float64, device=cuda)
-                fl.sweeps(backward, 2, tab2, dv, dd, dc, f_d,
-                          None if zero else u_d, out)
+                fl.sweeps(backward, dvals, dgrp, f_d, None if zero else u_d, out)
                 got = out.cpu().numpy()
                 assert np.all(got[:, nt:] == 0.0), 'pads must stay zero'
                 for t in (0, 7, nt - 1):
-                    a = coef[0][t] * vals[0] + coef[1][t] * vals[1]
+                    a = gvals[grp[t]]
                     u0 = np.zeros((n, 1)) if zero else U0[:, t:t + 1]
                     ref = _oracle(pat, a, F[:, t:t + 1], u0, nsw, backward)
                     assert rel(got[:, t:t + 1], ref) < 1e-13, (
-                        Js, capacity, generic, ngrp, nsw, backward, zero, t)
-        # K = 1: one matrix for every slice
+                        Js, capacity, generic, nsw, backward, zero, t)
+        # one group: the same matrix for every slice
         a = 4.0 * vals[0] + 0.3 * vals[1]
-        d = 4.0 * diags[0] + 0.3 * diags[1]
-        tab1 = fl.kind_table([a], [d])
         out = torch.empty((n, ld), dtype=torch.float64, device=cuda)
-        fl.sweeps(True, 1, tab1, [dvec(a)], [dvec(d)], [], f_d, u_d, out)
+        fl.sweeps(True, fl.values_for([a]), None, f_d, u_d, out)
         ref = _oracle(pat, a, F, U0, nsw, True)
         assert rel(out.cpu().numpy()[:, :nt], ref) < 1e-13

@@ -61,39 +61,35 @@ def main():
                reps=1)
         return
     u = torch.zeros_like(x.data)
-    for var in os.environ.get('GS_VARIANTS', '').split():
-        os.environ['STK_GS_VARIANT'] = var
-        timeit('gs sweep fwd finest var=%s' % var, lambda: check(lib().stk_mg_smooth(
-            fam.handle, top, 1, 0, ptr(ctxK.coef[0]), ptr(ctxK.coef[1]), ptr(x.data), ptr(u), ld,
-            stream())), 24)
-    os.environ.pop('STK_GS_VARIANT', None)
-    timeit('gs sweep fwd finest (K=2)', lambda: check(lib().stk_mg_smooth(
-        fam.handle, top, 1, 0, ptr(ctxK.coef[0]), ptr(ctxK.coef[1]), ptr(x.data), ptr(u), ld,
-        stream())), 24)
-    timeit('gs 3 sweeps fwd finest (K=2)', lambda: check(lib().stk_mg_smooth(
-        fam.handle, top, 3, 0, ptr(ctxK.coef[0]), ptr(ctxK.coef[1]), ptr(x.data), ptr(u), ld,
-        stream())), 72)
-    timeit('gs 3 sweeps bwd finest (K=2)', lambda: check(lib().stk_mg_smooth(
-        fam.handle, top, 3, 1, ptr(ctxK.coef[0]), ptr(ctxK.coef[1]), ptr(x.data), ptr(u), ld,
-        stream())), 72)
+    ctxP = heq.P._chain[0][1]  # the groups of P: one per wavelet level
+    hP, hK = ctxP.handle, ctxK.handle
+    timeit('gs sweep fwd finest (P groups)', lambda: check(lib().stk_mg_smooth(
+        hP, top, 1, 0, ptr(ctxP.group), ptr(x.data), ptr(u), ld, stream())), 24)
+    timeit('gs 3 sweeps fwd finest (P groups)', lambda: check(lib().stk_mg_smooth(
+        hP, top, 3, 0, ptr(ctxP.group), ptr(x.data), ptr(u), ld, stream())), 72)
+    timeit('gs 3 sweeps bwd finest (1 group)', lambda: check(lib().stk_mg_smooth(
+        hK, top, 3, 1, None, ptr(x.data), ptr(u), ld, stream())), 72)
     fl = fam._levels[top].get('fused')
     if fl is not None:
         lvh = fam._levels[top]
         print('fused program (fwd):', fl.programs[0].stats, flush=True)
-        tab2 = fl.kind_table(lvh['vals'], lvh['diags'])
-        dv = [torch.from_numpy(v).cuda() for v in lvh['vals']]
-        dd = [torch.from_numpy(np.ascontiguousarray(d)).cuda() for d in lvh['diags']]
+
+        def group_values(groups):
+            return [_project(lvh['keys'], fam._galerkin(fam.combined(g))[top],
+                             lvh['n'], lvh['pattern']) for g in groups]
+
+        from spacetime_fullgrid_parallel_b200.multigrid import _project
+        vP = fl.values_for(group_values(ctxP.groups))
+        vK = fl.values_for(group_values(ctxK.groups))
         u2 = torch.zeros_like(x.data)
-        timeit('FUSED gs 3 sweeps fwd zero-guess (K=2)', lambda: fl.sweeps(
-            False, 2, tab2, dv, dd, ctxK.coef, x.data, None, u2), 48)
-        timeit('FUSED gs 3 sweeps fwd (K=2)', lambda: fl.sweeps(
-            False, 2, tab2, dv, dd, ctxK.coef, x.data, u, u2), 72)
-        timeit('FUSED gs 3 sweeps bwd (K=2)', lambda: fl.sweeps(
-            True, 2, tab2, dv, dd, ctxK.coef, x.data, u, u2), 72)
-        a1 = lvh['vals'][1]
-        tab1 = fl.kind_table([a1], [lvh['diags'][1]])
-        timeit('FUSED gs 3 sweeps bwd (K=1)', lambda: fl.sweeps(
-            True, 1, tab1, [dv[1]], [dd[1]], [], x.data, u, u2), 72)
+        timeit('FUSED gs 3 sweeps fwd zero-guess (P groups)', lambda: fl.sweeps(
+            False, vP, ctxP.group, x.data, None, u2), 48)
+        timeit('FUSED gs 3 sweeps fwd (P groups)', lambda: fl.sweeps(
+            False, vP, ctxP.group, x.data, u, u2), 72)
+        timeit('FUSED gs 3 sweeps bwd (P groups)', lambda: fl.sweeps(
+            True, vP, ctxP.group, x.data, u, u2), 72)
+        timeit('FUSED gs 3 sweeps bwd (1 group)', lambda: fl.sweeps(
+            True, vK, None, x.data, u, u2), 72)
     if args.only == 'fused':
         timeit('MG K_x apply (2 V(3,3))', lambda: heq.Kinv_x.apply_block(x.data, y.data), 523)
         timeit('S apply', lambda: heq.S._matvec(x, y), 1300)
@@ -119,8 +115,8 @@ def main():
         u1 = torch.zeros((n1, ld), dtype=torch.float64, device='cuda')
         f1 = torch.rand((n1, ld), dtype=torch.float64, device='cuda')
         timeit('gs 3 sweeps fwd level-1', lambda: check(lib().stk_mg_smooth(
-            fam.handle, top - 1, 3, 0, ptr(ctxK.coef[0]), ptr(ctxK.coef[1]), ptr(f1), ptr(u1),
-            ld, stream())), 72 * n1 / heq.M)
+            hP, top - 1, 3, 0, ptr(ctxP.group), ptr(f1), ptr(u1), ld, stream())),
+            72 * n1 / heq.M)
     timeit('spmm A_x (K=1)', lambda: heq.A_x.spmm(x.data, y.data), 16)
     timeit('spmm M_x (K=1)', lambda: heq.M_x.spmm(x.data, y.data), 16)
     timeit('MG K_x apply (2 V(3,3))', lambda: heq.Kinv_x.apply_block(x.data, y.data), 523)

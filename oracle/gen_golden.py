@@ -82,9 +82,9 @@ def gen_multigrid():
     np.savez_compressed(os.path.join(GOLDEN, 'multigrid.npz'), **out)
 
 
-def graph_outputs(prob, mode, P=1, store_solution=True):
+def graph_outputs(prob, mode, P=1, store_solution=True, precond='multigrid'):
     """Runs on every emulated rank; returns rank-local pieces."""
-    g = ref_harness.RefGraph(prob, wavelettransform=mode)
+    g = ref_harness.RefGraph(prob, wavelettransform=mode, precond=precond)
     a, b = g.dofs_distr.t_begin, g.dofs_distr.t_end
     X = rand((prob.N, prob.M))[a:b]
     res = {}
@@ -114,8 +114,9 @@ def _graph_rank(args):
     Jt, Js, mode, store = args[:4]
     prob = (CubeProblem if len(args) > 4 and args[4] == 'cube' else
             SquareProblem)(Js, Jt)
+    precond = args[5] if len(args) > 5 else 'multigrid'
     with contextlib.redirect_stdout(io.StringIO()):
-        return graph_outputs(prob, mode, store_solution=store)
+        return graph_outputs(prob, mode, store_solution=store, precond=precond)
 
 
 def merge(parts):
@@ -175,6 +176,31 @@ def gen_cube():
     np.savez_compressed(os.path.join(GOLDEN, 'cube.npz'), **out)
 
 
+def gen_direct():
+    """precond='direct' (linop.py:18-26, heateq_mpi.py:154-157): the cases of
+    heateq_mpi_test.py:66-135 (J_time=4, J_space=2, 'original' and the default
+    wavelet transform) plus a two-rank one, from the reference classes."""
+    from mpi4py import MPI
+    from source.linop import InvLinOp
+    out = {}
+    for Jt, Js, mode, P in ((4, 2, 'original', 1), (4, 2, 'composite', 1),
+                            (3, 3, 'composite', 2)):
+        args = (Jt, Js, mode, True, 'square', 'direct')
+        res = _graph_rank(args) if P == 1 else merge(
+            MPI.launch(P, _graph_rank, args))
+        tag = 'direct_Jt%d_Js%d_%s_P%d' % (Jt, Js, mode, P)
+        print(tag, 'iters', res['iters'], 'norm_u', res['norm_u'])
+        for k, v in res.items():
+            out['%s__%s' % (tag, k)] = v
+    prob = SquareProblem(3, 2)
+    B = rand((prob.M, 3), seed=41)
+    for name, mat in (('A', prob.A_x), ('C1', prob.Cinv_j[1])):
+        inv = InvLinOp(mat)
+        out['inv_%s_J3' % name] = np.stack([inv @ B[:, k] for k in range(3)],
+                                           axis=1)
+    np.savez_compressed(os.path.join(GOLDEN, 'direct.npz'), **out)
+
+
 def gen_lanczos():
     from source.lanczos import Lanczos
     prob = SquareProblem(2, 3)
@@ -192,8 +218,12 @@ if __name__ == '__main__':
     if 'cube' in sys.argv[1:]:  # python -m oracle.gen_golden cube
         gen_cube()
         sys.exit(0)
+    if 'direct' in sys.argv[1:]:  # python -m oracle.gen_golden direct
+        gen_direct()
+        sys.exit(0)
     gen_wavelets()
     gen_multigrid()
     gen_lanczos()
     gen_graph()
     gen_cube()
+    gen_direct()

@@ -48,11 +48,11 @@ class RefGraph:
     """The objects HeatEquationMPI.__init__ builds after assembly, made of
     reference classes only."""
     def __init__(self, prob, wavelettransform='composite', smoothsteps=3,
-                 vcycles=2, comm=None):
+                 vcycles=2, comm=None, precond='multigrid'):
         activate()
         import numpy as np
         from mpi4py import MPI
-        from source.linop import CompositeLinOp
+        from source.linop import CompositeLinOp, InvLinOp
         from source.mpi_kron import (BlockDiagMPI, CompositeMPI,
                                      MatKronIdentityMPI, SumMPI,
                                      TridiagKronMatMPI)
@@ -75,8 +75,13 @@ class RefGraph:
             self.WT = MatKronIdentityMPI(d, self.W_t.T)
         h = p.hierarchy
         mg = dict(smoothsteps=smoothsteps, vcycles=vcycles)
-        self.Kinv_x = MultiGrid(p.A_x, h, **mg)  # heateq_mpi.py:144-147
-        self.C_j = [MultiGrid(mat, h, **mg) for mat in p.Cinv_j]
+        if precond == 'multigrid':
+            self.Kinv_x = MultiGrid(p.A_x, h, **mg)  # heateq_mpi.py:144-147
+            self.C_j = [MultiGrid(mat, h, **mg) for mat in p.Cinv_j]
+        else:  # heateq_mpi.py:154-157
+            assert precond == 'direct'
+            self.Kinv_x = InvLinOp(p.A_x)
+            self.C_j = [InvLinOp(mat) for mat in p.Cinv_j]
         self.CAC_j = [
             CompositeLinOp([C, p.A_x, C]) for C in self.C_j
         ]  # heateq_mpi.py:159-162

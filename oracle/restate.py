@@ -240,12 +240,30 @@ class MultiGridOracle:
         return np.ascontiguousarray(self(np.ascontiguousarray(B.T)).T)
 
 
+class InvOracle:
+    """Direct inverse on slice blocks X of shape (k, M): SuperLU with the
+    options of source/linop.py:18-26 (`InvLinOp`, precond='direct')."""
+    def __init__(self, mat):
+        import scipy.sparse.linalg as spla
+        self.lu = spla.splu(sp.csc_matrix(mat),
+                            options={"SymmetricMode": True},
+                            permc_spec="MMD_AT_PLUS_A")
+        self.shape = mat.shape
+
+    def __call__(self, X):
+        return np.ascontiguousarray(
+            self.lu.solve(np.ascontiguousarray(np.asarray(X).T)).T)
+
+    def __matmul__(self, B):
+        return self.lu.solve(np.asarray(B, dtype=np.float64))
+
+
 # ---------------------------------------------------------------------------
 # the operator graph of heateq_mpi.py:126-191
 # ---------------------------------------------------------------------------
 class HeatEqOracle:
     def __init__(self, prob, smoothsteps=3, vcycles=2, interleaved=True,
-                 threads=1):
+                 threads=1, precond='multigrid'):
         p = self.prob = prob
         P_mats = p.hierarchy.P_mats
         self.J = p.J_time
@@ -254,9 +272,14 @@ class HeatEqOracle:
         # thread, exactly like the reference's MPI ranks (mpi_vector.py:18-31);
         # the C kernels and SciPy's sparse products release the GIL.
         self.threads = threads
-        self.K = MultiGridOracle(p.A_x, P_mats, smoothsteps, vcycles)
-        self.C = [MultiGridOracle(m, P_mats, smoothsteps, vcycles)
-                  for m in p.Cinv_j]
+        if precond == 'multigrid':  # heateq_mpi.py:142-153
+            self.K = MultiGridOracle(p.A_x, P_mats, smoothsteps, vcycles)
+            self.C = [MultiGridOracle(m, P_mats, smoothsteps, vcycles)
+                      for m in p.Cinv_j]
+        else:  # heateq_mpi.py:154-157
+            assert precond == 'direct'
+            self.K = InvOracle(p.A_x)
+            self.C = [InvOracle(m) for m in p.Cinv_j]
         self.levels = wavelet_levels(self.J, interleaved)
         K, Mx, Ax = self.K, p.M_x, p.A_x
         self.terms = [  # heateq_mpi.py:166-178

@@ -26,7 +26,7 @@ from .linop import CompositeLinOp
 import scipy.sparse as sp
 import torch
 
-from .linop import DeviceCSRPair, as_space_op
+from .linop import DeviceCSRPair, InvLinOp, as_space_op
 from .mpi_kron import (BlockDiagMPI, CompositeMPI, LinearOperatorMPI,
                        MatKronIdentityMPI, SumMPI, TridiagKronMatMPI)
 from .timeop import TimeOpPlan, TimeOpPlan2
@@ -141,19 +141,24 @@ class HeatEquationMPI:
             self.WT = MatKronIdentityMPI(self.dofs_distr, self.W_t.T)
 
         # ---- preconditioners in space (heateq_mpi.py:142-162) ----
-        if precond != 'multigrid':
-            raise NotImplementedError(
-                "precond=%r: the device path implements 'multigrid' only" %
-                precond)
-        hierarchy = prob.hierarchy
-        from .mpi_vector import pitch
-        self.family = MultiGridFamily([prob.M_x, prob.A_x], hierarchy,
-                                      smoothsteps=smoothsteps, vcycles=vcycles,
-                                      ld_hint=pitch(self.dofs_distr.n_loc))
-        self.Kinv_x = self.family.member((0.0, 1.0))
-        self.C_j = [
-            self.family.member((2.0**j, alpha)) for j in range(J_time + 1)
-        ]
+        if precond == 'multigrid':
+            hierarchy = prob.hierarchy
+            from .mpi_vector import pitch
+            self.family = MultiGridFamily([prob.M_x, prob.A_x], hierarchy,
+                                          smoothsteps=smoothsteps,
+                                          vcycles=vcycles,
+                                          ld_hint=pitch(self.dofs_distr.n_loc))
+            self.Kinv_x = self.family.member((0.0, 1.0))
+            self.C_j = [
+                self.family.member((2.0**j, alpha)) for j in range(J_time + 1)
+            ]
+        else:
+            # exact inverses (heateq_mpi.py:154-157): host SuperLU factors,
+            # device triangular solves
+            assert precond == 'direct'
+            self.family = None
+            self.Kinv_x = InvLinOp(prob.A_x)
+            self.C_j = [InvLinOp(mat) for mat in prob.Cinv_j]
         self.CAC_j = [
             CompositeLinOp([self.C_j[j], self.A_x, self.C_j[j]])
             for j in range(J_time + 1)

@@ -164,6 +164,96 @@ class CompositeLinOp:
         return host_apply(self, B)
 
 
+def lu_factors(mat):
+    """Host factorisation behind `InvLinOp`: SuperLU with exactly the options
+    of linop.py:20-24, returned as sparse factors
+        Pr mat Pc = L U   (L unit lower, U upper triangular, CSR)
+    so that  mat^{-1} b = Pc U^{-1} L^{-1} Pr b."""
+    import scipy.sparse.linalg as spla
+    mat = sp.csc_matrix(mat, dtype=np.float64)
+    n = mat.shape[0]
+    lu = spla.splu(mat, options={'SymmetricMode': True},
+                   permc_spec='MMD_AT_PLUS_A')
+    one, idx = np.ones(n), np.arange(n)
+    Pr = sp.csr_matrix((one, (lu.perm_r, idx)), shape=(n, n))
+    Pc = sp.csr_matrix((one, (idx, lu.perm_c)), shape=(n, n))
+    return Pr, sp.csr_matrix(lu.L), sp.csr_matrix(lu.U), Pc
+
+
+class InvLinOp:
+    """Direct inverse of a sparse matrix as a space operator (linop.py:18-26,
+    the `precond='direct'` branch of heateq_mpi.py:154-157 and the exact-inverse
+    cross-check of heateq_mpi_test.py:66-135).
+
+    The factorisation is SuperLU's, once, on the host (as the reference); the
+    SOLVES run on the device for all time slices of a block at once.  A
+    triangular solve is the lexicographic Gauss-Seidel sweep of its factor --
+    forward for L, backward for U, exact after one sweep -- so it runs on the
+    smoother's wavefront kernels (`k_gs_phase`, one launch per level of the
+    factor's dependency DAG); the row/column permutations are one-entry-per-row
+    SpMMs."""
+    def __init__(self, mat, device=None):
+        from .multigrid import gauss_seidel_schedule
+        if device is None:
+            from .mpi_vector import _device
+            device = _device()
+        if isinstance(mat, DeviceCSR):
+            mat = mat.host
+        Pr, L, U, Pc = lu_factors(mat)
+        self.shape = Pr.shape
+        self.dtype = np.dtype(np.float64)
+        self.device = device
+        self.Pr, self.Pc = DeviceCSR(Pr, device), DeviceCSR(Pc, device)
+        self.num_applies = 0
+        self._keep = []
+        self._tri = []
+        for T in (L, U):
+            T.sort_indices()
+            order, phase_ptr = gauss_seidel_schedule(T.indptr, T.indices)
+            dev = [torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(device)
+                   for a, dt in ((T.indptr, np.int32), (T.indices, np.int32),
+                                 (T.data, np.float64),
+                                 (T.diagonal(), np.float64), (order, np.int32))]
+            import ctypes
+            h = ctypes.c_void_p(lib().stk_mg_create(2, 1, 1, 1))
+            assert h.value, 'stk_mg_create failed'
+            ip, ix, dv, dd, od = dev
+            check(lib().stk_mg_set_level(h, 1, T.shape[0], int(T.nnz), ptr(ip),
+                                         ptr(ix), ptr(dv), ptr(dd), ptr(od),
+                                         phase_ptr.ctypes.data,
+                                         len(phase_ptr) - 1))
+            self._keep.append(dev)
+            self._tri.append(h)
+        self.depth = None
+
+    def __del__(self):
+        try:
+            for h in self._tri:
+                lib().stk_mg_destroy(h)
+            self._tri = []
+        except Exception:
+            pass
+
+    def apply_block(self, x, out, ctx=None):
+        ld = x.shape[1]
+        a = torch.empty_like(x)
+        b = torch.zeros_like(x)
+        self.Pr.spmm(x, a)
+        # L b = a (forward sweep from b = 0), U a = b (backward sweep from a = 0)
+        check(lib().stk_mg_smooth(self._tri[0], 1, 1, 0, None, ptr(a), ptr(b),
+                                  ld, stream()))
+        a.zero_()
+        check(lib().stk_mg_smooth(self._tri[1], 1, 1, 1, None, ptr(b), ptr(a),
+                                  ld, stream()))
+        self.Pc.spmm(a, out)
+        self.num_applies += 1
+
+    def __matmul__(self, B):
+        return host_apply(self, B)
+
+    matvec = matmat = dot = __matmul__
+
+
 class KronLinOp:
     """Serial (mat_time (x) mat_space) x on a host vector of N*M entries
     (linop.py:6-15), computed on the device."""

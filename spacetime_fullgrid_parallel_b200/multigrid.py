@@ -187,8 +187,21 @@ def gauss_seidel_schedule(indptr, indices, return_wave=False):
     indptr = np.ascontiguousarray(indptr, dtype=np.int32)
     indices = np.ascontiguousarray(indices, dtype=np.int32)
     wave = np.zeros(max(n, 1), dtype=np.int32)
-    depth = lib().stk_gs_wavefronts(n, indptr.ctypes.data,
-                                    indices.ctypes.data, wave.ctypes.data)
+    # A row must come after every lower-numbered row it is coupled to IN EITHER
+    # DIRECTION (row j > i reads u_i, and row i reads u_j: neither may overtake
+    # the other), so the wavefronts come from the symmetrised pattern; for the
+    # structurally symmetric FE matrices that is the pattern itself.
+    pat = sp.csr_matrix((np.ones(len(indices), dtype=np.int8), indices, indptr),
+                        shape=(n, n))
+    sym = (pat + pat.T).tocsr()
+    if sym.nnz != pat.nnz:
+        sym.sort_indices()
+        wp = np.ascontiguousarray(sym.indptr, dtype=np.int32)
+        wi = np.ascontiguousarray(sym.indices, dtype=np.int32)
+    else:
+        wp, wi = indptr, indices
+    depth = lib().stk_gs_wavefronts(n, wp.ctypes.data, wi.ctypes.data,
+                                    wave.ctypes.data)
     wave = wave[:n]
     # Rows of a wavefront are independent, so their order is free: sort them by
     # their highest-numbered neighbour.  With hierarchical numberings the

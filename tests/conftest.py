@@ -31,7 +31,7 @@ def rel(a, b):
 def golden():
     return {
         name: np.load(os.path.join(GOLDEN, name + '.npz'))
-        for name in ('wavelets', 'multigrid', 'graph', 'lanczos', 'cube')
+        for name in ('wavelets', 'multigrid', 'graph', 'lanczos', 'cube', 'direct')
     }
 
 

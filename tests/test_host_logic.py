@@ -261,6 +261,39 @@ def test_wavefront_sweep_equals_sequential_sweep():
             assert rel(u, ref) < 1e-13
 
 
+def test_triangular_solves_as_wavefront_sweeps():
+    """`InvLinOp` (linop.py:18-26) on the device = SuperLU's factors applied by
+    the smoother's wavefront kernels: one forward sweep on L and one backward
+    sweep on U are exact triangular solves.  The factors are NOT structurally
+    symmetric, so the wavefronts must come from the symmetrised pattern."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    from spacetime_fullgrid_parallel_b200.linop import lu_factors
+    from spacetime_fullgrid_parallel_b200.multigrid import gauss_seidel_schedule
+    prob = SquareProblem(3, 1)
+    A = prob.Cinv_j[1]
+    Pr, L, U, Pc = lu_factors(A)
+    assert abs(Pr @ A @ Pc - L @ U).max() < 1e-13
+    b = rand((A.shape[0], 2), seed=3)
+    cur = Pr @ b
+    for T, backward in ((L, False), (U, True)):
+        T = sp.csr_matrix(T)
+        T.sort_indices()
+        rows, phase_ptr = gauss_seidel_schedule(T.indptr, T.indices)
+        assert len(phase_ptr) - 1 > 1
+        diag = T.diagonal()
+        u = np.zeros_like(cur)
+        order = range(len(phase_ptr) - 1)
+        for ph in (reversed(order) if backward else order):
+            sel = rows[phase_ptr[ph]:phase_ptr[ph + 1]]
+            u[sel] += (cur[sel] - (T[sel] @ u)) / diag[sel][:, None]
+        cur = u
+    x = Pc @ cur
+    ref = spla.splu(sp.csc_matrix(A), options={'SymmetricMode': True},
+                    permc_spec='MMD_AT_PLUS_A').solve(b)
+    assert rel(x, ref) < 1e-13
+
+
 def test_chained_wavelet_all_ranks_with_exchange():
     """W and W^T over ALL ranks of a decomposition through the chain, with the
     halo exchange and its adjoint emulated exactly as `fetch` /

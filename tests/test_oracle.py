@@ -129,6 +129,28 @@ def test_graph_golden(golden):
         assert abs(np.linalg.norm(u) - float(g[tag + '__norm_u'])) < 1e-10
 
 
+def test_direct_golden(golden):
+    """precond='direct' (linop.py:18-26, heateq_mpi.py:154-157): the oracle
+    against outputs of the reference classes -- the cases of
+    heateq_mpi_test.py:66-135 (J_time=4, J_space=2) and a two-rank one."""
+    g = golden['direct']
+    prob = SquareProblem(3, 2)
+    B = rand((prob.M, 3), seed=41)
+    for name, mat in (('A', prob.A_x), ('C1', prob.Cinv_j[1])):
+        assert rel(orc.InvOracle(mat) @ B, g['inv_%s_J3' % name]) < 1e-13
+    for Jt, Js, inter, tag in ((4, 2, False, 'direct_Jt4_Js2_original_P1'),
+                               (4, 2, True, 'direct_Jt4_Js2_composite_P1'),
+                               (3, 3, True, 'direct_Jt3_Js3_composite_P2')):
+        prob = SquareProblem(Js, Jt)
+        o = orc.HeatEqOracle(prob, interleaved=inter, precond='direct')
+        X = rand((prob.N, prob.M))
+        for name in ('W', 'S', 'WT', 'P', 'WT_S_W'):
+            assert rel(getattr(o, name)(X), g['%s__%s' % (tag, name)]) < 1e-12
+        w, iters = o.solve()
+        assert iters == int(g[tag + '__iters'])
+        assert rel(w, g[tag + '__w']) < 1e-10
+
+
 def test_config1_norms(golden):
     """BASELINE config 1/2 (J_time=3, J_space=6): norms of the big fields."""
     g = golden['graph']

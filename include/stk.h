@@ -94,6 +94,18 @@ int stk_space_spmm(int nrows, const int *indptr, const int *indices, int K,
                    double alpha, double beta, const double *z, double *y,
                    int ld, void *stream);
 
+/* Row schedule of a CSR structure for all stk_space_spmm* entry points (and the
+ * SpMMs inside stk_mg_apply): `order` (device, nrows entries, a permutation of
+ * the rows) is the order in which the kernels walk the rows of the matrix
+ * whose row-pointer array is `indptr`; NULL removes it.  Results do not depend
+ * on it -- rows are independent -- only DRAM traffic does: with a hierarchical
+ * FE numbering the index order sweeps the mesh once per vertex class and
+ * re-fetches every x row each time; a locality order (reverse Cuthill-McKee of
+ * the pattern, computed at setup) walks the mesh once.  The reference has no
+ * counterpart (scipy's csr_matvecs walks rows in index order,
+ * mpi_kron.py:149); remove the order before freeing `indptr`. */
+int stk_csr_set_row_order(const int *indptr, int nrows, const int *order);
+
 /* ---- time operator: sparse matrix along the time axis -------------------
  * mpi_kron.py:186-201 (TridiagKronIdentityMPI), :285-317
  * (SparseKronIdentityMPI), :240-256 (MatKronIdentityMPI after permute).

@@ -32,6 +32,7 @@ SIGNATURES = {
         _int, _vp, _vp, _int, _vp, _vp, _vp, _vp, _vp, _dbl, _dbl, _vp, _vp,
         _int, _vp
     ]),
+    'stk_csr_set_row_order': (_int, [_vp, _int, _vp]),
     'stk_time_apply': (_int, [
         _int, _int, _int, _vp, _vp, _vp, _vp, _int, _int, _vp, _int, _dbl,
         _dbl, _vp, _int, _vp

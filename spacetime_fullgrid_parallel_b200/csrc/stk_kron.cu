@@ -21,12 +21,13 @@ __global__ void __launch_bounds__(256)
                  const double *__restrict__ vals0, const double *__restrict__ vals1,
                  const double *__restrict__ coef0, const double *__restrict__ coef1,
                  const double *__restrict__ x, double alpha, double beta, const double *z,
-                 double *y, int ld, unsigned ld2) {
+                 double *y, int ld, unsigned ld2, const int *__restrict__ rows) {
     const unsigned total = (unsigned)nrows * ld2;
     const unsigned stride = gridDim.x * 256u;
     for (unsigned k = blockIdx.x * 256u + threadIdx.x; k < total; k += stride) {
-        unsigned i = k / ld2;
-        unsigned c = (k - i * ld2) * 2u;
+        const unsigned r = k / ld2;
+        unsigned c = (k - r * ld2) * 2u;
+        const unsigned i = rows ? (unsigned)__ldg(rows + r) : r;
         int p0 = __ldg(indptr + i), p1 = __ldg(indptr + i + 1);
         double2 s0 = make_double2(0.0, 0.0), s1 = make_double2(0.0, 0.0);
         row_product<K>(p0, p1, indices, vals0, vals1, x, ld, c, s0, s1);
@@ -59,12 +60,13 @@ __global__ void __launch_bounds__(256)
     k_space_spmm_g(int nrows, const int *__restrict__ indptr, const int *__restrict__ indices,
                    const double *__restrict__ vals, size_t vstride, const int *__restrict__ grp,
                    const double *__restrict__ x, double alpha, double beta, const double *z,
-                   double *y, int ld, unsigned ld2) {
+                   double *y, int ld, unsigned ld2, const int *__restrict__ rows) {
     const unsigned total = (unsigned)nrows * ld2;
     const unsigned stride = gridDim.x * 256u;
     for (unsigned k = blockIdx.x * 256u + threadIdx.x; k < total; k += stride) {
-        unsigned i = k / ld2;
-        unsigned c = (k - i * ld2) * 2u;
+        const unsigned r = k / ld2;
+        unsigned c = (k - r * ld2) * 2u;
+        const unsigned i = rows ? (unsigned)__ldg(rows + r) : r;
         const double *v0 = vals + (size_t)__ldg(grp + c) * vstride;
         const double *v1 = vals + (size_t)__ldg(grp + c + 1) * vstride;
         int p1 = __ldg(indptr + i + 1);
@@ -203,12 +205,14 @@ __global__ void __launch_bounds__(256)
     k_space_spmm_split(int nrows, const int *__restrict__ indptr, const int *__restrict__ indices,
                        const double *__restrict__ vals0, const double *__restrict__ vals1,
                        const double *__restrict__ x, double *__restrict__ y0,
-                       double *__restrict__ y1, int ld, unsigned ld2) {
+                       double *__restrict__ y1, int ld, unsigned ld2,
+                       const int *__restrict__ rows) {
     const unsigned total = (unsigned)nrows * ld2;
     const unsigned stride = gridDim.x * 256u;
     for (unsigned k = blockIdx.x * 256u + threadIdx.x; k < total; k += stride) {
-        unsigned i = k / ld2;
-        unsigned c = (k - i * ld2) * 2u;
+        const unsigned r = k / ld2;
+        unsigned c = (k - r * ld2) * 2u;
+        const unsigned i = rows ? (unsigned)__ldg(rows + r) : r;
         int p0 = __ldg(indptr + i), p1 = __ldg(indptr + i + 1);
         double2 s0 = make_double2(0.0, 0.0), s1 = make_double2(0.0, 0.0);
         row_product<2>(p0, p1, indices, vals0, vals1, x, ld, c, s0, s1);
@@ -226,12 +230,13 @@ __global__ void __launch_bounds__(256)
                       const double *__restrict__ vals0, const double *__restrict__ vals1,
                       const double *__restrict__ x0, const double *__restrict__ x1, int ldx,
                       double alpha, double beta, const double *z, double *y, int ld,
-                      unsigned ld2) {
+                      unsigned ld2, const int *__restrict__ rows) {
     const unsigned total = (unsigned)nrows * ld2;
     const unsigned stride = gridDim.x * 256u;
     for (unsigned k = blockIdx.x * 256u + threadIdx.x; k < total; k += stride) {
-        unsigned i = k / ld2;
-        unsigned c = (k - i * ld2) * 2u;
+        const unsigned r = k / ld2;
+        unsigned c = (k - r * ld2) * 2u;
+        const unsigned i = rows ? (unsigned)__ldg(rows + r) : r;
         int p1 = __ldg(indptr + i + 1);
         double2 s = make_double2(0.0, 0.0);
         for (int p = __ldg(indptr + i); p < p1; ++p) {
@@ -378,6 +383,24 @@ __global__ void __launch_bounds__(256)
     x[o] = (beta == 0.0) ? alpha * in[k] : fma(alpha, in[k], beta * x[o]);
 }
 
+// Row schedules (stk_csr_set_row_order): the space SpMMs are free to walk the
+// rows of a matrix in any order; with a hierarchical FE numbering the index
+// order visits the mesh several times over (one pass per vertex class), so
+// every x row is fetched from DRAM once per pass.  A locality order registered
+// for the CSR structure (keyed by its row-pointer array) makes the kernels
+// walk the mesh once: neighbouring rows are re-read from L2.
+struct RowOrder {
+    int nrows;
+    const int *order;
+};
+static std::unordered_map<const void *, RowOrder> g_row_orders;
+
+const int *row_order_for(const int *indptr, int nrows) {
+    if (g_row_orders.empty()) return nullptr;
+    auto it = g_row_orders.find((const void *)indptr);
+    return (it != g_row_orders.end() && it->second.nrows == nrows) ? it->second.order : nullptr;
+}
+
 int launch_space_spmm(int nrows, const int *indptr, const int *indices, int K,
                       const double *vals0, const double *vals1, const double *coef0,
                       const double *coef1, const double *x, double alpha, double beta,
@@ -390,7 +413,8 @@ int launch_space_spmm(int nrows, const int *indptr, const int *indices, int K,
     if (has_z && z == nullptr) return fail(-1, "stk_space_spmm: beta != 0 needs z");
 #define STK_SPMM(KK, ZZ)                                                                     \
     k_space_spmm<KK, ZZ><<<resident_grid(k_space_spmm<KK, ZZ>, 256, work), 256, 0, s>>>(     \
-        nrows, indptr, indices, vals0, vals1, coef0, coef1, x, alpha, beta, z, y, ld, ld2)
+        nrows, indptr, indices, vals0, vals1, coef0, coef1, x, alpha, beta, z, y, ld, ld2, rows)
+    const int *rows = row_order_for(indptr, nrows);
     if (K == 1) {
         if (has_z) STK_SPMM(1, true); else STK_SPMM(1, false);
     } else {
@@ -412,12 +436,13 @@ int launch_space_spmm_grouped(int nrows, const int *indptr, const int *indices,
     int64_t work = (int64_t)nrows * ld2;
     if (work >= STK_MAX_ITEMS) return fail(-2, "stk_space_spmm: block too large for 32-bit grid");
     if (beta != 0.0 && z == nullptr) return fail(-1, "stk_space_spmm: beta != 0 needs z");
+    const int *rows = row_order_for(indptr, nrows);
     if (beta != 0.0)
         k_space_spmm_g<true><<<resident_grid(k_space_spmm_g<true>, 256, work), 256, 0, s>>>(
-            nrows, indptr, indices, vals, vstride, grp, x, alpha, beta, z, y, ld, ld2);
+            nrows, indptr, indices, vals, vstride, grp, x, alpha, beta, z, y, ld, ld2, rows);
     else
         k_space_spmm_g<false><<<resident_grid(k_space_spmm_g<false>, 256, work), 256, 0, s>>>(
-            nrows, indptr, indices, vals, vstride, grp, x, alpha, beta, z, y, ld, ld2);
+            nrows, indptr, indices, vals, vstride, grp, x, alpha, beta, z, y, ld, ld2, rows);
     return check_launch("k_space_spmm_g");
 }
 
@@ -426,6 +451,15 @@ int launch_space_spmm_grouped(int nrows, const int *indptr, const int *indices,
 using namespace stk;
 
 extern "C" {
+
+int stk_csr_set_row_order(const int *indptr, int nrows, const int *order) {
+    if (!indptr) return fail(-1, "stk_csr_set_row_order: null row pointer");
+    if (!order)
+        g_row_orders.erase((const void *)indptr);
+    else
+        g_row_orders[(const void *)indptr] = RowOrder{nrows, order};
+    return 0;
+}
 
 int stk_space_spmm(int nrows, const int *indptr, const int *indices, int K, const double *vals0,
                    const double *vals1, const double *coef0, const double *coef1,
@@ -531,7 +565,7 @@ int stk_space_spmm_split(int nrows, const int *indptr, const int *indices, const
     if (work >= STK_MAX_ITEMS) return fail(-2, "stk_space_spmm_split: block too large");
     k_space_spmm_split<<<resident_grid(k_space_spmm_split, 256, work), 256, 0,
                          as_stream(stream)>>>(nrows, indptr, indices, vals0, vals1, x, y0, y1, ld,
-                                              ld2);
+                                              ld2, row_order_for(indptr, nrows));
     return check_launch("k_space_spmm_split");
 }
 
@@ -548,13 +582,14 @@ int stk_space_spmm_pair(int nrows, const int *indptr, const int *indices, const 
     int64_t work = (int64_t)nrows * ld2;
     if (work >= STK_MAX_ITEMS) return fail(-2, "stk_space_spmm_pair: block too large");
     cudaStream_t s = as_stream(stream);
+    const int *rows = row_order_for(indptr, nrows);
     if (beta != 0.0)
         k_space_spmm_pair<true><<<resident_grid(k_space_spmm_pair<true>, 256, work), 256, 0, s>>>(
-            nrows, indptr, indices, vals0, vals1, x0, x1, ldx, alpha, beta, z, y, ld, ld2);
+            nrows, indptr, indices, vals0, vals1, x0, x1, ldx, alpha, beta, z, y, ld, ld2, rows);
     else
         k_space_spmm_pair<false><<<resident_grid(k_space_spmm_pair<false>, 256, work), 256, 0,
                                    s>>>(nrows, indptr, indices, vals0, vals1, x0, x1, ldx, alpha,
-                                        beta, z, y, ld, ld2);
+                                        beta, z, y, ld, ld2, rows);
     return check_launch("k_space_spmm_pair");
 }
 

@@ -20,10 +20,57 @@ import torch
 from ._lib import check, lib, ptr, stream
 
 
+def locality_order(pattern):
+    """Row order in which neighbouring rows of a (square, structurally
+    symmetrised) sparsity pattern are visited close together: reverse
+    Cuthill-McKee.  Setup only; any permutation is valid for the kernels."""
+    from scipy.sparse.csgraph import reverse_cuthill_mckee
+    pat = sp.csr_matrix(pattern)
+    n = pat.shape[0]
+    if n < 2 or pat.shape[0] != pat.shape[1]:
+        return None
+    g = sp.csr_matrix((np.ones(pat.nnz, dtype=np.int8), pat.indices,
+                       pat.indptr), shape=pat.shape)
+    return np.ascontiguousarray(
+        reverse_cuthill_mckee((g + g.T).tocsr(), symmetric_mode=True),
+        dtype=np.int32)
+
+
+def row_order_enabled():
+    import os
+    return os.environ.get('STK_ROW_ORDER', '1') != '0'
+
+
+class _RowOrder:
+    """Keeps a device row schedule registered for a CSR row-pointer array
+    (stk_csr_set_row_order) for as long as the owner lives."""
+    def __init__(self, indptr_dev, nrows, order, device):
+        self.indptr = indptr_dev
+        self.order = None
+        if order is None or not row_order_enabled():
+            return
+        order = np.ascontiguousarray(order, dtype=np.int32)
+        assert len(order) == nrows
+        self.order = torch.from_numpy(order).to(device)
+        check(lib().stk_csr_set_row_order(ptr(indptr_dev), int(nrows),
+                                          ptr(self.order)))
+
+    def __del__(self):
+        try:
+            if self.order is not None:
+                lib().stk_csr_set_row_order(ptr(self.indptr), 0, None)
+        except Exception:
+            pass
+
+
+# below this many rows the whole block stays in L2 whatever the order
+ROW_ORDER_MIN_ROWS = 16384
+
+
 class DeviceCSR:
     """A CSR matrix resident in HBM (fp64 values, int32 indices, as
     mpi_shared_mem.py:46-48 stores them)."""
-    def __init__(self, mat, device=None):
+    def __init__(self, mat, device=None, row_order='auto'):
         mat = sp.csr_matrix(mat, dtype=np.float64)
         mat.sort_indices()
         if device is None:
@@ -36,6 +83,14 @@ class DeviceCSR:
         self.indices = torch.from_numpy(mat.indices.astype(np.int32)).to(device)
         self.data = torch.from_numpy(mat.data.astype(np.float64)).to(device)
         self.num_applies = 0
+        # row schedule of the SpMM kernels: 'auto' = a locality order for
+        # large square matrices, None = index order, or an explicit permutation
+        if isinstance(row_order, str):
+            row_order = (locality_order(mat)
+                         if mat.shape[0] >= ROW_ORDER_MIN_ROWS
+                         and row_order_enabled() else None)
+        self._row_order = _RowOrder(self.indptr, mat.shape[0], row_order,
+                                    device)
 
     def spmm(self, x, out, alpha=1.0, beta=0.0, z=None):
         """out = alpha * A x + beta * z  on blocks; z may be out."""
@@ -93,6 +148,10 @@ class DeviceCSRPair:
         self.indptr = torch.from_numpy(pat.indptr.astype(np.int32)).to(device)
         self.indices = torch.from_numpy(pat.indices.astype(np.int32)).to(device)
         self.vals0, self.vals1 = project(m0), project(m1)
+        self._row_order = _RowOrder(
+            self.indptr, pat.shape[0],
+            locality_order(pat) if pat.shape[0] >= ROW_ORDER_MIN_ROWS
+            and row_order_enabled() else None, device)
 
     def split(self, x, y0, y1):
         """y0 = mat0 x, y1 = mat1 x."""

@@ -22,7 +22,8 @@ import torch
 
 from . import gs_program
 from ._lib import check, lib, ptr, stream
-from .linop import host_apply
+from .linop import (ROW_ORDER_MIN_ROWS, _RowOrder, host_apply, locality_order,
+                    row_order_enabled)
 from .mpi_vector import _device
 
 MAX_COARSE = 1024
@@ -284,6 +285,7 @@ class MultiGridFamily:
         self._keep = []  # device tensors shared by the handles
         self.num_phases = []
         self._levels = []
+        self._orders = []  # registered row schedules (kept alive)
 
         def up(a, dt):
             t = torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(dev)
@@ -316,7 +318,13 @@ class MultiGridFamily:
                                        dev).multi_processor_count)
                 if not fused.ok:
                     fused = None
+            # row schedules of the level's SpMMs (residual; prolongation walks
+            # the fine rows, restriction the coarse rows, in their levels'
+            # locality orders)
+            loc = (locality_order(pat)
+                   if n >= ROW_ORDER_MIN_ROWS and row_order_enabled() else None)
             lv = {'n': n, 'nnz': int(pat.nnz), 'pattern': pat, 'keys': keys,
+                  'locality': loc,
                   'indptr': up(pat.indptr, np.int32),
                   'indices': up(pat.indices, np.int32),
                   'order': up(order, np.int32), 'phase_ptr': phase_ptr,
@@ -329,6 +337,11 @@ class MultiGridFamily:
                 lv['transfer'] = [up(P.indptr, np.int32), up(P.indices, np.int32),
                                   up(P.data, np.float64), up(R.indptr, np.int32),
                                   up(R.indices, np.int32), up(R.data, np.float64)]
+                self._orders.append(_RowOrder(lv['transfer'][0], n, loc, dev))
+                self._orders.append(_RowOrder(lv['transfer'][3], R.shape[0],
+                                              self._levels[l - 1]['locality'],
+                                              dev))
+            self._orders.append(_RowOrder(lv['indptr'], n, loc, dev))
             self._levels.append(lv)
 
     def _galerkin(self, mat):

@@ -88,6 +88,48 @@ def test_space_spmm_family_and_modes(cuda, n_t, M):
     assert b'alias' in L.stk_last_error()
 
 
+def test_row_order_changes_nothing_but_the_walk(cuda):
+    """stk_csr_set_row_order: every SpMM entry point gives bit-identical
+    results with a registered row schedule (rows are independent), for the
+    plain, residual (z), split and pair forms; removal restores index order."""
+    torch, check, L, ptr, pitch = _env()
+    n_t, M = 9, 257
+    ld = pitch(n_t)
+    rs = np.random.RandomState(5)
+    A0 = sp.random(M, M, density=0.05, random_state=rs, format='csr') + sp.identity(M)
+    ip, ix, v0, A = _csr(torch, A0)
+    v1 = torch.from_numpy(rs.rand(A.nnz)).cuda()
+    x, z = _block(torch, rs.rand(n_t, M), ld), _block(torch, rs.rand(n_t, M), ld)
+
+    def run_all():
+        y = [torch.full((M, ld), np.nan, dtype=torch.float64, device='cuda') for _ in range(5)]
+        check(L.stk_space_spmm(M, ptr(ip), ptr(ix), 1, ptr(v0), None, None, None, ptr(x), 1.0,
+                               0.0, None, ptr(y[0]), ld, None))
+        check(L.stk_space_spmm(M, ptr(ip), ptr(ix), 1, ptr(v0), None, None, None, ptr(x), 1.0,
+                               -1.0, ptr(z), ptr(y[1]), ld, None))
+        check(L.stk_space_spmm_split(M, ptr(ip), ptr(ix), ptr(v0), ptr(v1), ptr(x), ptr(y[2]),
+                                     ptr(y[3]), ld, None))
+        check(L.stk_space_spmm_pair(M, ptr(ip), ptr(ix), ptr(v0), ptr(v1), ptr(x), ptr(z), ld,
+                                    1.0, 0.0, None, ptr(y[4]), ld, None))
+        return [t.cpu().numpy() for t in y]
+
+    base = run_all()
+    assert rel(base[0][:, :n_t], A @ x.cpu().numpy()[:, :n_t]) < 1e-14
+    order = torch.from_numpy(rs.permutation(M).astype(np.int32)).cuda()
+    check(L.stk_csr_set_row_order(ptr(ip), M, ptr(order)))
+    try:
+        for a, b in zip(base, run_all()):
+            assert np.array_equal(a, b)
+        # an order registered for another row count is ignored, not misapplied
+        check(L.stk_csr_set_row_order(ptr(ip), M - 1, ptr(order)))
+        for a, b in zip(base, run_all()):
+            assert np.array_equal(a, b)
+    finally:
+        check(L.stk_csr_set_row_order(ptr(ip), 0, None))
+    for a, b in zip(base, run_all()):
+        assert np.array_equal(a, b)
+
+
 @pytest.mark.parametrize('dense', [False, True])
 def test_time_apply_with_halo(cuda, dense):
     """Local columns + slice-major halo columns, overwrite and accumulate,

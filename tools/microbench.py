@@ -95,6 +95,36 @@ def main():
         timeit('S apply', lambda: heq.S._matvec(x, y), 1300)
         timeit('P apply', lambda: heq.P._matvec(x, y), 1100)
         return
+    if args.only == 'ncu':
+        # one launch of every hot kernel at the bench size, for `ncu --set full`
+        # (tools/ncu_r2.sh): fused smoother fwd/bwd, residual, restriction,
+        # prolongation + correction, A_x / split / pair, time stencil, wavelets
+        import scipy.sparse as sp
+        from spacetime_fullgrid_parallel_b200.linop import DeviceCSR
+        lvl = fam._levels[top]
+        Ptop = DeviceCSR(sp.csr_matrix(fam.hierarchy.P_mats[top - 1]))
+        Rtop = DeviceCSR(sp.csr_matrix(fam.hierarchy.R_mats[top - 1]))
+        nc = Ptop.shape[1]
+        uc = torch.rand((nc, ld), dtype=torch.float64, device='cuda')
+        fc = torch.empty_like(uc)
+        z = x.copy()
+        S = heq.S
+        mx, ax = x.empty_like(), x.empty_like()
+        z1 = torch.empty_like(x.data)
+        steps = [
+            ('residual A u - f', lambda: heq.A_x.spmm(x.data, y.data, 1.0, -1.0, z.data), 24),
+            ('restriction', lambda: Rtop.spmm(x.data, fc), 10),
+            ('prolongation + correction', lambda: Ptop.spmm(uc, y.data, -1.0, 1.0, y.data), 18),
+            ('spmm A_x', lambda: heq.A_x.spmm(x.data, y.data), 16),
+            ('S: split', lambda: S.MA.split(x.data, mx.data, ax.data), 24),
+            ('S: bracket', lambda: S.bracket1.apply(mx, ax, y.data), 24),
+            ('S: pair', lambda: S.MA.pair(mx.data, ax.data, z1), 24),
+            ('wavelet W', lambda: heq.W._matvec(x, y), 16),
+            ('wavelet WT', lambda: heq.WT._matvec(x, y), 16),
+        ]
+        for name, fn, b in steps:
+            timeit(name, fn, b, reps=1)
+        return
     if args.only in ('gs', 'synth'):
         import scipy.sparse as sp
         from spacetime_fullgrid_parallel_b200.linop import DeviceCSR

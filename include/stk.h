@@ -71,6 +71,14 @@ int stk_xpay(const double *x, double a, double *y, int64_t n, void *stream);
 /* w += a*p ; r -= a*t  in one pass (linalg.py:29-30). */
 int stk_pcg_update(double a, const double *p, const double *t, double *w,
                    double *r, int64_t n, void *stream);
+/* The same two updates with the scalar a = num_dev[0] / den_dev[0] read on the
+ * device: alpha = r.z / p.t and beta = r.z / (r.z)_old of linalg.py:27,38 never
+ * visit the host, so a PCG iteration has one read-back (the stop test). */
+int stk_xpay_dev(const double *x, const double *num_dev, const double *den_dev,
+                 double *y, int64_t n, void *stream);
+int stk_pcg_update_dev(const double *num_dev, const double *den_dev,
+                       const double *p, const double *t, double *w, double *r,
+                       int64_t n, void *stream);
 /* out_dev[0] = sum_k x[k]*y[k], single pass, deterministic: per-CTA
  * warp-shuffle partials, the last CTA adds them in index order
  * (mpi_vector.py:205-210 local np.dot; the allreduce is the caller's).

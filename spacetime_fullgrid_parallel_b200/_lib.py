@@ -27,6 +27,8 @@ SIGNATURES = {
     'stk_scale': (_int, [_dbl, _vp, _i64, _vp]),
     'stk_xpay': (_int, [_vp, _dbl, _vp, _i64, _vp]),
     'stk_pcg_update': (_int, [_dbl, _vp, _vp, _vp, _vp, _i64, _vp]),
+    'stk_xpay_dev': (_int, [_vp, _vp, _vp, _vp, _i64, _vp]),
+    'stk_pcg_update_dev': (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     'stk_dot': (_int, [_vp, _vp, _i64, _vp, _vp, _vp]),
     'stk_space_spmm': (_int, [
         _int, _vp, _vp, _int, _vp, _vp, _vp, _vp, _vp, _dbl, _dbl, _vp, _vp,

@@ -68,6 +68,13 @@ class SerialComm:
         # a rank never messages itself in the plans built by timeop.py
         assert not sends and not recvs
 
+    def exchange_begin(self, sends, recvs):
+        assert not sends and not recvs
+        return []
+
+    def exchange_end(self, reqs):
+        pass
+
     def all_to_all(self, send_chunks, recv_chunks):
         recv_chunks[0].copy_(send_chunks[0])
 
@@ -120,6 +127,14 @@ class TorchComm:
     def exchange(self, sends, recvs):
         """sends / recvs: {peer: contiguous tensor}.  All transfers are posted
         as one batch (a single NCCL group) and waited for."""
+        self.exchange_end(self.exchange_begin(sends, recvs))
+
+    def exchange_begin(self, sends, recvs):
+        """Posts the batch and returns its requests without waiting: with NCCL
+        the transfers run on the communicator's own stream, ordered after the
+        work already enqueued on the current stream; what the caller enqueues
+        before `exchange_end` overlaps them (the `callback` of
+        mpi_vector.py:155-183)."""
         ops = []
         for peer in sorted(recvs):
             ops.append(self.dist.P2POp(self.dist.irecv, recvs[peer], peer,
@@ -127,9 +142,14 @@ class TorchComm:
         for peer in sorted(sends):
             ops.append(self.dist.P2POp(self.dist.isend, sends[peer], peer,
                                        self.group))
-        if ops:
-            for req in self.dist.batch_isend_irecv(ops):
-                req.wait()
+        self.bytes_sent = getattr(self, 'bytes_sent', 0) + sum(
+            t.numel() * t.element_size() for t in sends.values())
+        return self.dist.batch_isend_irecv(ops) if ops else []
+
+    def exchange_end(self, reqs):
+        """The current stream (NCCL) / the host (gloo) waits for the batch."""
+        for req in reqs:
+            req.wait()
 
     def all_to_all(self, send_chunks, recv_chunks):
         """send_chunks[p] goes to rank p, recv_chunks[p] comes from rank p."""

@@ -51,8 +51,13 @@ __global__ void __launch_bounds__(256) k_scale(double a, double *__restrict__ x,
     }
 }
 
+// num != nullptr: the scalar is num[0] / den[0], read on the device (Krylov
+// coefficients that never visit the host).
 __global__ void __launch_bounds__(256) k_xpay(const double *__restrict__ x, double a,
-                                              double *__restrict__ y, int64_t n2) {
+                                              double *__restrict__ y, int64_t n2,
+                                              const double *__restrict__ num,
+                                              const double *__restrict__ den) {
+    if (num) a = __ldg(num) / __ldg(den);
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n2; k += stride) {
         double2 xv = ldv2(x + 2 * k), yv = ldv2(y + 2 * k);
@@ -64,7 +69,9 @@ __global__ void __launch_bounds__(256) k_xpay(const double *__restrict__ x, doub
 
 __global__ void __launch_bounds__(256)
     k_pcg_update(double a, const double *__restrict__ p, const double *__restrict__ t,
-                 double *__restrict__ w, double *__restrict__ r, int64_t n2) {
+                 double *__restrict__ w, double *__restrict__ r, int64_t n2,
+                 const double *__restrict__ num, const double *__restrict__ den) {
+    if (num) a = __ldg(num) / __ldg(den);
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n2; k += stride) {
         double2 pv = ldv2(p + 2 * k), tv = ldv2(t + 2 * k);
@@ -193,7 +200,16 @@ int stk_scale(double a, double *x, int64_t n, void *stream) {
 int stk_xpay(const double *x, double a, double *y, int64_t n, void *stream) {
     if (n & 1) return fail(-1, "stk_xpay: n must be even");
     if (n == 0) return 0;
-    k_xpay<<<stream_grid(n / 2), 256, 0, as_stream(stream)>>>(x, a, y, n / 2);
+    k_xpay<<<stream_grid(n / 2), 256, 0, as_stream(stream)>>>(x, a, y, n / 2, nullptr, nullptr);
+    return check_launch("k_xpay");
+}
+
+int stk_xpay_dev(const double *x, const double *num, const double *den, double *y, int64_t n,
+                 void *stream) {
+    if (n & 1) return fail(-1, "stk_xpay_dev: n must be even");
+    if (!num || !den) return fail(-1, "stk_xpay_dev: null scalar");
+    if (n == 0) return 0;
+    k_xpay<<<stream_grid(n / 2), 256, 0, as_stream(stream)>>>(x, 0.0, y, n / 2, num, den);
     return check_launch("k_xpay");
 }
 
@@ -201,7 +217,18 @@ int stk_pcg_update(double a, const double *p, const double *t, double *w, double
                    int64_t n, void *stream) {
     if (n & 1) return fail(-1, "stk_pcg_update: n must be even");
     if (n == 0) return 0;
-    k_pcg_update<<<stream_grid(n / 2), 256, 0, as_stream(stream)>>>(a, p, t, w, r, n / 2);
+    k_pcg_update<<<stream_grid(n / 2), 256, 0, as_stream(stream)>>>(a, p, t, w, r, n / 2,
+                                                                    nullptr, nullptr);
+    return check_launch("k_pcg_update");
+}
+
+int stk_pcg_update_dev(const double *num, const double *den, const double *p, const double *t,
+                       double *w, double *r, int64_t n, void *stream) {
+    if (n & 1) return fail(-1, "stk_pcg_update_dev: n must be even");
+    if (!num || !den) return fail(-1, "stk_pcg_update_dev: null scalar");
+    if (n == 0) return 0;
+    k_pcg_update<<<stream_grid(n / 2), 256, 0, as_stream(stream)>>>(0.0, p, t, w, r, n / 2, num,
+                                                                    den);
     return check_launch("k_pcg_update");
 }
 

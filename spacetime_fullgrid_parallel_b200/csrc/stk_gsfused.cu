@@ -232,13 +232,16 @@ __global__ void __launch_bounds__(NT, 1) k_gs_fused(const GsArgs a) {
 
     int ld_beg = (m0 > 0) ? __ldg(&a.step_info[m0 - 1].y) : 0;
     int2 info = __ldg(a.step_info + m0);
+    // the step table is read two steps ahead: the next step's entry is needed
+    // right after this step's loads are issued (no exposed L2 latency)
+    int2 info_nx = (m0 + 1 < m1) ? __ldg(a.step_info + m0 + 1) : info;
     int2 ldpf = make_int2(0, 0);
     if (ld_beg + grp < info.y) ldpf = __ldg(a.lds + ld_beg + grp);
     int p = p0;
     __syncthreads();  // tables ready
 
     for (int m = m0; m < m1; ++m) {
-        const int2 info_nx = (m + 1 < m1) ? __ldg(a.step_info + m + 1) : info;
+        const int2 info_nn = (m + 2 < m1) ? __ldg(a.step_info + m + 2) : info_nx;
         // 1. window loads of this step (visible LOOKAHEAD + 1 steps later); they
         //    join the cp.async group of the step's first pass
         if (ld_beg + grp < info.y) {
@@ -267,29 +270,36 @@ __global__ void __launch_bounds__(NT, 1) k_gs_fused(const GsArgs a) {
             const unsigned self = h.w & 0xffffu;
             double2 s = make_double2(0.0, 0.0), uo = make_double2(0.0, 0.0), rd;
             if (!GEN) {
-                // fixed trip count, entry 0 = the diagonal (u_i itself)
-                const bool bulk = BULK && (int)h.z == a.bulk_kind;
-                const double *kv0 = vtab + (g0 * a.nkinds + h.z) * ks;
-                const double *kv1 = GROUPED ? vtab + (g1 * a.nkinds + h.z) * ks : kv0;
+                // fixed trip count, entry 0 = the diagonal (u_i itself).  Almost
+                // every row is of the bulk kind: its own branch keeps the table
+                // reads and the register/table selects out of that path (rows of
+                // one warp rarely mix kinds, so the branch seldom diverges).
+                if (BULK && (int)h.z == a.bulk_kind) {
 #pragma unroll
-                for (int e = 0; e < (NNZ ? NNZ : 8); ++e) {
-                    if (NNZ == 0 && e >= a.maxnnz) break;
-                    const unsigned sl = slot_of(nb, e);
-                    const double2 xv = *reinterpret_cast<const double2 *>(win + sl * T + woff);
-                    if (e == 0) uo = xv;
-                    double a0, a1;
-                    if (bulk) {
-                        a0 = b0[BULK ? e : 0];
-                        a1 = b1[BULK ? e : 0];
-                    } else {
-                        a0 = kv0[e];
-                        a1 = GROUPED ? kv1[e] : a0;
+                    for (int e = 0; e < NB; ++e) {
+                        const unsigned sl = slot_of(nb, e);
+                        const double2 xv = *reinterpret_cast<const double2 *>(win + sl * T + woff);
+                        if (e == 0) uo = xv;
+                        s.x = fma(b0[e], xv.x, s.x);
+                        s.y = fma(b1[e], xv.y, s.y);
                     }
-                    s.x = fma(a0, xv.x, s.x);
-                    s.y = fma(a1, xv.y, s.y);
+                    rd = brd;
+                } else {
+                    const double *kv0 = vtab + (g0 * a.nkinds + h.z) * ks;
+                    const double *kv1 = GROUPED ? vtab + (g1 * a.nkinds + h.z) * ks : kv0;
+#pragma unroll
+                    for (int e = 0; e < (NNZ ? NNZ : 8); ++e) {
+                        if (NNZ == 0 && e >= a.maxnnz) break;
+                        const unsigned sl = slot_of(nb, e);
+                        const double2 xv = *reinterpret_cast<const double2 *>(win + sl * T + woff);
+                        if (e == 0) uo = xv;
+                        const double a0 = kv0[e];
+                        const double a1 = GROUPED ? kv1[e] : a0;
+                        s.x = fma(a0, xv.x, s.x);
+                        s.y = fma(a1, xv.y, s.y);
+                    }
+                    rd = *reinterpret_cast<const double2 *>(rdiag + (unsigned)h.z * RS + woff);
                 }
-                rd = bulk ? brd
-                          : *reinterpret_cast<const double2 *>(rdiag + (unsigned)h.z * RS + woff);
             } else {
                 const double *c0 = a.cvals + (size_t)g0 * a.vstride + h.z;
                 const double *c1 = a.cvals + (size_t)g1 * a.vstride + h.z;
@@ -331,6 +341,7 @@ __global__ void __launch_bounds__(NT, 1) k_gs_fused(const GsArgs a) {
         if (threadIdx.x == 0) feed(p);
         ld_beg = info.y;
         info = info_nx;
+        info_nx = info_nn;
     }
     cp_async_wait<0>();
 }

@@ -9,6 +9,8 @@
 // so every load of x[j, :] and every store of y[i, :] is a contiguous
 // 16-byte-per-lane access and the CSR row (indices, values) is a warp-uniform
 // broadcast load that is read once for all time slices.
+#include <stdlib.h>
+
 #include "stk_common.cuh"
 
 namespace stk {
@@ -47,6 +49,48 @@ __global__ void __launch_bounds__(256)
             out.y = alpha * s0.y;
         }
         stv2(y + o, out);
+    }
+}
+
+// Single-matrix form with FOUR time values per thread (256-bit loads and
+// stores): the broadcast loads of the CSR row (index + value per entry) are
+// shared by twice as many outputs, which is what bounds these kernels once the
+// row schedule has removed the DRAM re-reads (L1 data path 72 % busy with two
+// values per thread, profiles/r2c_ncu_summary.md).  Needs ld % 4 == 0 and
+// 32-byte aligned blocks (the pitch rule; checked by the callers).
+template <bool HAS_Z>
+__global__ void __launch_bounds__(256)
+    k_space_spmm4(int nrows, const int *__restrict__ indptr, const int *__restrict__ indices,
+                  const double *__restrict__ vals, const double *__restrict__ x, double alpha,
+                  double beta, const double *z, double *y, int ld, unsigned ld4,
+                  const int *__restrict__ rows) {
+    const unsigned total = (unsigned)nrows * ld4;
+    const unsigned stride = gridDim.x * 256u;
+    for (unsigned k = blockIdx.x * 256u + threadIdx.x; k < total; k += stride) {
+        const unsigned r = k / ld4;
+        const unsigned c = (k - r * ld4) * 4u;
+        const unsigned i = rows ? (unsigned)__ldg(rows + r) : r;
+        const int p1 = __ldg(indptr + i + 1);
+        double4v s = {0.0, 0.0, 0.0, 0.0};
+        for (int p = __ldg(indptr + i); p < p1; ++p) {
+            const double4v xv = ldv4(x + (size_t)__ldg(indices + p) * ld + c);
+            fma4(__ldg(vals + p), xv, s);
+        }
+        const size_t o = (size_t)i * ld + c;
+        double4v out;
+        if (HAS_Z) {
+            const double4v zv = ldv4(z + o);
+            out.x = fma(alpha, s.x, beta * zv.x);
+            out.y = fma(alpha, s.y, beta * zv.y);
+            out.z = fma(alpha, s.z, beta * zv.z);
+            out.w = fma(alpha, s.w, beta * zv.w);
+        } else {
+            out.x = alpha * s.x;
+            out.y = alpha * s.y;
+            out.z = alpha * s.z;
+            out.w = alpha * s.w;
+        }
+        stv4(y + o, out);
     }
 }
 
@@ -415,6 +459,22 @@ int launch_space_spmm(int nrows, const int *indptr, const int *indices, int K,
     k_space_spmm<KK, ZZ><<<resident_grid(k_space_spmm<KK, ZZ>, 256, work), 256, 0, s>>>(     \
         nrows, indptr, indices, vals0, vals1, coef0, coef1, x, alpha, beta, z, y, ld, ld2, rows)
     const int *rows = row_order_for(indptr, nrows);
+    static const bool wide = [] {  // STK_SPMM_WIDE=0: two values per thread
+        const char *e = getenv("STK_SPMM_WIDE");
+        return !(e && e[0] == '0');
+    }();
+    const bool aligned = (((uintptr_t)x | (uintptr_t)y | (uintptr_t)z) & 31u) == 0;
+    if (K == 1 && wide && aligned && (ld & 3) == 0) {
+        const unsigned ld4 = (unsigned)ld / 4u;
+        const int64_t work4 = (int64_t)nrows * ld4;
+        if (has_z)
+            k_space_spmm4<true><<<resident_grid(k_space_spmm4<true>, 256, work4), 256, 0, s>>>(
+                nrows, indptr, indices, vals0, x, alpha, beta, z, y, ld, ld4, rows);
+        else
+            k_space_spmm4<false><<<resident_grid(k_space_spmm4<false>, 256, work4), 256, 0, s>>>(
+                nrows, indptr, indices, vals0, x, alpha, beta, z, y, ld, ld4, rows);
+        return check_launch("k_space_spmm4");
+    }
     if (K == 1) {
         if (has_z) STK_SPMM(1, true); else STK_SPMM(1, false);
     } else {

@@ -65,13 +65,27 @@ class SchurOperatorMPI(LinearOperatorMPI):
         self.plans = plans
         self.bracket1 = TimeOpPlan2(plans['A'], plans['L'])
         self.bracket2 = TimeOpPlan2(plans['LT'], plans['M'])
+        # all four tridiagonal stencils move the same +-1 slices
+        assert len({plans[k]._key for k in ('A', 'L', 'LT', 'M')}) == 1
+        self.overlap = os.environ.get('STK_OVERLAP', '1') != '0'
 
     def _matvec(self, vec_in, vec_out):
         assert vec_in is not vec_out
         c0 = sum(getattr(p, 'time_communication', 0.0)
                  for p in self.plans.values())
         mx, ax = vec_in.empty_like(), vec_in.empty_like()
-        self.MA.split(vec_in.data, mx.data, ax.data)  # M x and A x, one pass
+        halo_plan = self.plans['A']
+        if halo_plan.n_halo and self.overlap:
+            # the time stencils need the neighbours' boundary slices of M x and
+            # A x: fetch those slices of x instead -- posted first, in flight
+            # while the local products run -- and apply M and A to them here
+            # (half the bytes, and no exchange on the critical path)
+            halo = halo_plan.fetch(
+                vec_in, callback=lambda: self.MA.split(vec_in.data, mx.data,
+                                                       ax.data))
+            halo_plan.halo_of_image(halo, self.MA, mx, ax)
+        else:
+            self.MA.split(vec_in.data, mx.data, ax.data)  # M x, A x: one pass
         # the two brackets side by side in one block of pitch 2*ld, so that K
         # solves for both in ONE batched V-cycle (twice the columns per launch:
         # what keeps narrow time slabs on many GPUs efficient)

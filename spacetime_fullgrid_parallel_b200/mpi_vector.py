@@ -256,13 +256,18 @@ class KronVectorMPI:
                             ptr(ws), ptr(out), stream()))
         return out
 
+    def dot_global_device(self, other):
+        """Global dot product as a one-element device tensor of its own: the
+        local reduction, then the scalar allreduce, nothing read back."""
+        out = self.dot_device(other).clone()
+        if self.dofs_distr.size > 1:
+            out = self.dofs_distr.comm.allreduce_sum(out)
+        return out
+
     def dot(self, other):
         """Global dot product (mpi_vector.py:205-210): fused single-pass local
         reduction, then one allreduce of the device scalar over NCCL."""
-        out = self.dot_device(other)
-        if self.dofs_distr.size > 1:
-            out = self.dofs_distr.comm.allreduce_sum(out.clone())
-        return float(out.item())
+        return float(self.dot_global_device(other).item())
 
     # -- root <-> slabs (mpi_vector.py:124-138; tests/as_global_matrix) ---
     def scatter(self, X_glob):

@@ -114,14 +114,46 @@ class TimeOpPlan:
             sends[p] = buf
         for p, (off, cnt) in self.recv_from.items():
             recvs[p] = halo[off:off + cnt]
-        if callback is not None:
-            callback()
+        # post the transfers, run the caller's independent work while they are
+        # in flight, then make the stream wait (mpi_vector.py:155-183)
         t0 = _now()
-        vec.dofs_distr.comm.exchange(sends, recvs)
+        comm = vec.dofs_distr.comm
+        reqs = comm.exchange_begin(sends, recvs)
+        if callback is not None:
+            self.time_communication = getattr(self, 'time_communication',
+                                              0.0) + _now() - t0
+            callback()
+            t0 = _now()
+        comm.exchange_end(reqs)
         self.time_communication = getattr(self, 'time_communication',
                                           0.0) + _now() - t0
         vec._halo[key] = halo
         return halo
+
+    def halo_of_image(self, halo, pair, out0, out1):
+        """Halo slices of M x and A x from the halo slices of x: space
+        operators act slice by slice, so the neighbours' boundary slices of
+        (I (x) M) x are M applied to their boundary slices of x.  `halo`:
+        (n_halo, M) slice-major; `pair`: a DeviceCSRPair; returns two
+        slice-major buffers that `out0._halo` / `out1._halo` then hold for
+        this plan's exchange pattern (one exchange of x instead of two of its
+        images, issued before the products it overlaps)."""
+        import torch
+        from ._lib import check, lib, ptr, stream
+        from .mpi_vector import pitch
+        nh, M = halo.shape
+        ldh = pitch(nh)
+        dev = halo.device
+        blk = torch.empty((M, ldh), dtype=torch.float64, device=dev)
+        check(lib().stk_block_from_rowmajor(ptr(halo), nh, M, ptr(blk), ldh,
+                                            stream()))
+        b0, b1 = torch.empty_like(blk), torch.empty_like(blk)
+        pair.split(blk, b0, b1)
+        for b, vec in ((b0, out0), (b1, out1)):
+            h = torch.empty((nh, M), dtype=torch.float64, device=dev)
+            check(lib().stk_block_to_rowmajor(ptr(b), ldh, nh, M, ptr(h),
+                                              stream()))
+            vec._halo[self._key] = h
 
     def apply(self, vec_in, out_block, alpha=1.0, beta=0.0):
         """out_block = alpha * (T (x) I) vec_in + beta * out_block."""

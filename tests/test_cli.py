@@ -50,10 +50,33 @@ def test_flags_match_the_reference_defaults():
     assert t.wavelettransform == 'original' and t.iters == 3  # heateq_mpi_timing.py:35-42
 
 
+def _host_pcg(T, P, b, callback=None, eps=1e-6):
+    """NumPy stand-in for the device PCG (the product has no host form): only
+    here so that the driver's report can be checked without a GPU."""
+    w = np.zeros_like(b)
+    r = b.copy()
+    p = P @ r
+    rz = r @ p
+    iters = 0
+    while rz >= eps * eps:
+        iters += 1
+        t = T @ p
+        a = rz / (p @ t)
+        w += a * p
+        r -= a * t
+        if callback is not None:
+            callback(w, r, iters)
+        z = P @ r
+        rz, rz_old = r @ z, rz
+        p = z + (rz / rz_old) * p
+    return w, iters
+
+
 def test_driver_main_report_and_blob(monkeypatch, capsys):
     import torch
     monkeypatch.setattr(torch.cuda, 'synchronize', lambda *a, **k: None)
     monkeypatch.setattr(_cli, 'build', lambda args, comm: _FakeHeatEq())
+    monkeypatch.setattr(heateq_mpi, 'PCG', _host_pcg)
     u, iters = heateq_mpi.main(['--J_time', '2', '--J_space', '1'])
     out = capsys.readouterr().out
     assert 'Completed in {} PCG steps.'.format(iters) in out and 'N = 5. M = 7.' in out

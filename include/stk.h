@@ -278,7 +278,13 @@ int stk_gs_fused(const stk_gs_prog *prog, int G, int T, const double *ktab,
  * stk_mg_apply. */
 int stk_mg_set_fused(stk_mg *mg, int level, const stk_gs_prog *fwd,
                      const stk_gs_prog *bwd, const double *ktab, int nkinds,
-                     int bulk_kind, const double *cvals, int T);
+                     int bulk_kind, const double *cvals, int T, int kstride,
+                     const int *kind_of_row, const int *canon_indices);
+/* With a kind table (kstride = maxnnz + 2 doubles per kind), kind_of_row[nrows]
+ * and canon_indices[nnz] (the level's column indices in the table's entry
+ * order, device arrays, may be NULL) also serve the level's grouped residual
+ * A_{g(t)} u - f (multigrid.py:174): the G matrices are read from the table in
+ * shared memory instead of G value arrays in HBM. */
 /* HOST helper (host pointers): interval colouring of window lifetimes
  * [start[q], end[q]] (macro-steps); slot[q] out; returns the slots used. */
 int stk_gs_alloc_slots(int n, const int *start, const int *end, int *slot);

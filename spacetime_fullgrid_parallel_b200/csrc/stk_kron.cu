@@ -134,6 +134,69 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// Grouped SpMM through ROW KINDS (gs_program.row_kinds): on a uniformly refined
+// mesh the rows of a level carry a handful of distinct value sequences, so the
+// G group matrices are a table tab[g][kind][entry] of a few KB in shared
+// memory instead of G value arrays in HBM.  k_space_spmm_g fetches one matrix
+// value per (entry, time value) through L1 -- with one group per wavelet
+// level, the 64 columns a warp covers hit ~9 arrays per entry and those loads,
+// not x, bound the kernel (3.2 ms for the finest-level residual against 1.2 ms
+// single-matrix).  Here a thread owns four time values (256-bit x loads), reads
+// the row's kind once and its four groups' values from the table.  cidx lists
+// the column indices in the table's entry order (diagonal first).
+template <bool HAS_Z>
+__global__ void __launch_bounds__(256)
+    k_space_spmm_gk(int nrows, const int *__restrict__ indptr, const int *__restrict__ cidx,
+                    const int *__restrict__ kind_of_row, const double *__restrict__ ktab, int G,
+                    int nkinds, int kstride, const int *__restrict__ grp,
+                    const double *__restrict__ x, double alpha, double beta, const double *z,
+                    double *y, int ld, unsigned ld4, const int *__restrict__ rows) {
+    extern __shared__ double s_tab[];
+    const unsigned ks = (kstride & 1) ? kstride : kstride + 1;  // odd: banks spread
+    for (int k = threadIdx.x; k < G * nkinds * kstride; k += 256) {
+        const int row = k / kstride;
+        s_tab[row * ks + (k - row * kstride)] = __ldg(ktab + k);
+    }
+    __syncthreads();
+    const unsigned total = (unsigned)nrows * ld4;
+    const unsigned stride = gridDim.x * 256u;
+    for (unsigned k = blockIdx.x * 256u + threadIdx.x; k < total; k += stride) {
+        const unsigned r = k / ld4;
+        const unsigned c = (k - r * ld4) * 4u;
+        const unsigned i = rows ? (unsigned)__ldg(rows + r) : r;
+        const int4 g = __ldg(reinterpret_cast<const int4 *>(grp + c));
+        const unsigned kind = (unsigned)__ldg(kind_of_row + i);
+        const double *t0 = s_tab + ((unsigned)g.x * nkinds + kind) * ks;
+        const double *t1 = s_tab + ((unsigned)g.y * nkinds + kind) * ks;
+        const double *t2 = s_tab + ((unsigned)g.z * nkinds + kind) * ks;
+        const double *t3 = s_tab + ((unsigned)g.w * nkinds + kind) * ks;
+        const int p0 = __ldg(indptr + i), n = __ldg(indptr + i + 1) - p0;
+        double4v s = {0.0, 0.0, 0.0, 0.0};
+        for (int e = 0; e < n; ++e) {
+            const double4v xv = ldv4(x + (size_t)__ldg(cidx + p0 + e) * ld + c);
+            s.x = fma(t0[e], xv.x, s.x);
+            s.y = fma(t1[e], xv.y, s.y);
+            s.z = fma(t2[e], xv.z, s.z);
+            s.w = fma(t3[e], xv.w, s.w);
+        }
+        const size_t o = (size_t)i * ld + c;
+        double4v out;
+        if (HAS_Z) {
+            const double4v zv = ldv4(z + o);
+            out.x = fma(alpha, s.x, beta * zv.x);
+            out.y = fma(alpha, s.y, beta * zv.y);
+            out.z = fma(alpha, s.z, beta * zv.z);
+            out.w = fma(alpha, s.w, beta * zv.w);
+        } else {
+            out.x = alpha * s.x;
+            out.y = alpha * s.y;
+            out.z = alpha * s.z;
+            out.w = alpha * s.w;
+        }
+        stv4(y + o, out);
+    }
+}
+
 // One row of T against the time column of space dof i.
 __device__ __forceinline__ double time_row(int t, const int *__restrict__ indptr,
                                            const int *__restrict__ indices,
@@ -504,6 +567,33 @@ int launch_space_spmm_grouped(int nrows, const int *indptr, const int *indices,
         k_space_spmm_g<false><<<resident_grid(k_space_spmm_g<false>, 256, work), 256, 0, s>>>(
             nrows, indptr, indices, vals, vstride, grp, x, alpha, beta, z, y, ld, ld2, rows);
     return check_launch("k_space_spmm_g");
+}
+
+// Grouped SpMM with the groups' values given as a row-kind table; returns 1 if
+// the arguments do not allow it (the caller then uses the value arrays).
+int launch_space_spmm_kinds(int nrows, const int *indptr, const int *cidx,
+                            const int *kind_of_row, const double *ktab, int G, int nkinds,
+                            int kstride, const int *grp, const double *x, double alpha,
+                            double beta, const double *z, double *y, int ld, cudaStream_t s) {
+    if (!grp || !cidx || !kind_of_row || !ktab || (ld & 3)) return 1;
+    if ((((uintptr_t)x | (uintptr_t)y | (uintptr_t)z) & 31u) || ((uintptr_t)grp & 15u)) return 1;
+    const size_t smem = sizeof(double) * (size_t)G * nkinds * (kstride | 1);
+    if (smem > 40 * 1024) return 1;
+    if (nrows == 0) return 0;
+    const unsigned ld4 = (unsigned)ld / 4u;
+    const int64_t work = (int64_t)nrows * ld4;
+    if (work >= STK_MAX_ITEMS) return fail(-2, "stk_space_spmm: block too large for 32-bit grid");
+    if (beta != 0.0 && z == nullptr) return fail(-1, "stk_space_spmm: beta != 0 needs z");
+    const int *rows = row_order_for(indptr, nrows);
+    if (beta != 0.0)
+        k_space_spmm_gk<true><<<resident_grid(k_space_spmm_gk<true>, 256, work), 256, smem, s>>>(
+            nrows, indptr, cidx, kind_of_row, ktab, G, nkinds, kstride, grp, x, alpha, beta, z, y,
+            ld, ld4, rows);
+    else
+        k_space_spmm_gk<false><<<resident_grid(k_space_spmm_gk<false>, 256, work), 256, smem, s>>>(
+            nrows, indptr, cidx, kind_of_row, ktab, G, nkinds, kstride, grp, x, alpha, beta, z, y,
+            ld, ld4, rows);
+    return check_launch("k_space_spmm_gk");
 }
 
 }  // namespace stk

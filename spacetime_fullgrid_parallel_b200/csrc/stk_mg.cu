@@ -30,6 +30,10 @@ int launch_space_spmm_grouped(int nrows, const int *indptr, const int *indices,
                               const double *vals, size_t vstride, const int *grp, const double *x,
                               double alpha, double beta, const double *z, double *y, int ld,
                               cudaStream_t s);
+int launch_space_spmm_kinds(int nrows, const int *indptr, const int *cidx,
+                            const int *kind_of_row, const double *ktab, int G, int nkinds,
+                            int kstride, const int *grp, const double *x, double alpha,
+                            double beta, const double *z, double *y, int ld, cudaStream_t s);
 }  // namespace stk
 struct stk_gs_prog;
 namespace stk {
@@ -54,7 +58,10 @@ struct Level {
     const stk_gs_prog *fused_fwd = nullptr, *fused_bwd = nullptr;
     const double *ktab = nullptr;   // [G][nkinds][maxnnz + 2] (programs with kinds)
     const double *cvals = nullptr;  // [G][nnz], program entry order (generic programs)
-    int nkinds = 0, bulk_kind = -1, fused_T = 8;
+    int nkinds = 0, bulk_kind = -1, fused_T = 8, kstride = 0;
+    // row kinds of the level (programs with kinds): the grouped residual reads
+    // the groups' values from ktab instead of vals
+    const int *kind_of_row = nullptr, *canon_indices = nullptr;
 };
 
 // u_i += (f_i - A_i . u) / a_ii for the rows of one wavefront
@@ -120,6 +127,166 @@ __global__ void __launch_bounds__(256)
     u[(size_t)i * ld + t] = s;
 }
 
+// ---- the coarse levels of the V-cycle in ONE launch -----------------------
+// Below some level every kernel of the cycle is a few microseconds of work and
+// the cycle is a chain of ~30 dependent launches per level (one per Gauss-Seidel
+// wavefront): launch latency, the same on every slab width -- what limits
+// narrow time slabs (8 GPUs) first.  Time slices are independent, so one CTA
+// takes a chunk of MGC_T slices through the WHOLE cycle below level `top`
+// (multigrid.py:168-182 for j <= top, zero initial guess unless `u_in`):
+// u and f of every level live in shared memory, a wavefront / residual /
+// transfer is a block-synchronised phase instead of a launch, and the level
+// matrices come through L1.  The arithmetic of every row is that of the
+// per-level kernels (k_gs_phase, k_space_spmm, k_coarse_solve).
+constexpr int MGC_T = 4;         // time values per CTA
+constexpr int MGC_NT = 512;      // threads: 256 row lanes x 2 column pairs
+constexpr int MGC_MAXLV = 8;
+
+struct CoarseLevel {
+    int n, nnz, nph;
+    const int *indptr, *indices, *sched, *phase_ptr;  // phase_ptr: device copy
+    const double *vals, *diag;
+    const int *p_indptr, *p_indices, *r_indptr, *r_indices;
+    const double *p_vals, *r_vals;
+    int off_u, off_f;  // shared-memory offsets in rows of MGC_T doubles
+};
+struct CoarseArgs {
+    CoarseLevel L[MGC_MAXLV];
+    int top, nu, off_res, ld;
+    const double *inv;  // [G][n0][n0]
+    const int *grp;
+    const double *f, *u_in;
+    double *u;
+};
+
+template <bool GROUPED>
+__global__ void __launch_bounds__(MGC_NT, 1) k_mg_coarse(const CoarseArgs a) {
+    extern __shared__ __align__(16) double sm[];
+    const int half = threadIdx.x & 1;    // which pair of the chunk's 4 columns
+    const int lane = threadIdx.x >> 1;   // row lane
+    constexpr int NL = MGC_NT / 2;
+    const int c = blockIdx.x * MGC_T + 2 * half;
+    const bool valid = c < a.ld;
+    size_t g0 = 0, g1 = 0;
+    if (GROUPED && valid) {
+        g0 = (size_t)__ldg(a.grp + c);
+        g1 = (size_t)__ldg(a.grp + c + 1);
+    }
+    auto at = [&](int off, int row) -> double2 * {
+        return reinterpret_cast<double2 *>(sm + ((size_t)(off + row) * MGC_T + 2 * half));
+    };
+    const double2 zero2 = make_double2(0.0, 0.0);
+    const int top = a.top;
+    {   // right-hand side (and the initial guess) of the top level
+        const CoarseLevel &lv = a.L[top];
+        for (int i = lane; i < lv.n; i += NL) {
+            *at(lv.off_f, i) = valid ? ldv2(a.f + (size_t)i * a.ld + c) : zero2;
+            *at(lv.off_u, i) =
+                (valid && a.u_in) ? ldv2(a.u_in + (size_t)i * a.ld + c) : zero2;
+        }
+    }
+    __syncthreads();
+    // one Gauss-Seidel sweep of level lv, wavefront by wavefront
+    auto sweep = [&](const CoarseLevel &lv, bool backward) {
+        const double *v0 = lv.vals + g0 * (size_t)lv.nnz, *v1 = lv.vals + g1 * (size_t)lv.nnz;
+        const double *d0 = lv.diag + g0 * (size_t)lv.n, *d1 = lv.diag + g1 * (size_t)lv.n;
+        for (int q = 0; q < lv.nph; ++q) {
+            const int ph = backward ? lv.nph - 1 - q : q;
+            const int r0 = __ldg(lv.phase_ptr + ph), r1 = __ldg(lv.phase_ptr + ph + 1);
+            for (int r = r0 + lane; r < r1; r += NL) {
+                const int i = __ldg(lv.sched + r);
+                const int p1 = __ldg(lv.indptr + i + 1);
+                double2 s = zero2;
+                for (int p = __ldg(lv.indptr + i); p < p1; ++p) {
+                    const double2 xv = *at(lv.off_u, __ldg(lv.indices + p));
+                    const double a0 = __ldg(v0 + p);
+                    s.x = fma(a0, xv.x, s.x);
+                    s.y = fma(GROUPED ? __ldg(v1 + p) : a0, xv.y, s.y);
+                }
+                const double2 fv = *at(lv.off_f, i);
+                double2 uo = *at(lv.off_u, i);
+                uo.x += (fv.x - s.x) / __ldg(d0 + i);
+                uo.y += (fv.y - s.y) / __ldg(d1 + i);
+                *at(lv.off_u, i) = uo;
+            }
+            __syncthreads();
+        }
+    };
+    // ---- down: smooth, residual, restrict ----
+    for (int l = top; l >= 1; --l) {
+        const CoarseLevel &lv = a.L[l];
+        const CoarseLevel &lc = a.L[l - 1];
+        for (int sw = 0; sw < a.nu; ++sw) sweep(lv, false);
+        const double *v0 = lv.vals + g0 * (size_t)lv.nnz, *v1 = lv.vals + g1 * (size_t)lv.nnz;
+        for (int i = lane; i < lv.n; i += NL) {  // res = A u - f
+            const int p1 = __ldg(lv.indptr + i + 1);
+            double2 s = zero2;
+            for (int p = __ldg(lv.indptr + i); p < p1; ++p) {
+                const double2 xv = *at(lv.off_u, __ldg(lv.indices + p));
+                const double a0 = __ldg(v0 + p);
+                s.x = fma(a0, xv.x, s.x);
+                s.y = fma(GROUPED ? __ldg(v1 + p) : a0, xv.y, s.y);
+            }
+            const double2 fv = *at(lv.off_f, i);
+            *at(a.off_res, i) = make_double2(s.x - fv.x, s.y - fv.y);
+        }
+        __syncthreads();
+        for (int i = lane; i < lc.n; i += NL) {  // f_c = R res, u_c = 0
+            const int p1 = __ldg(lv.r_indptr + i + 1);
+            double2 s = zero2;
+            for (int p = __ldg(lv.r_indptr + i); p < p1; ++p) {
+                const double2 xv = *at(a.off_res, __ldg(lv.r_indices + p));
+                const double w = __ldg(lv.r_vals + p);
+                s.x = fma(w, xv.x, s.x);
+                s.y = fma(w, xv.y, s.y);
+            }
+            *at(lc.off_f, i) = s;
+            *at(lc.off_u, i) = zero2;
+        }
+        __syncthreads();
+    }
+    {   // level 0: exact solve with the dense inverse
+        const CoarseLevel &l0 = a.L[0];
+        const int n0 = l0.n;
+        const double *i0 = a.inv + g0 * (size_t)n0 * n0, *i1 = a.inv + g1 * (size_t)n0 * n0;
+        for (int i = lane; i < n0; i += NL) {
+            double2 s = zero2;
+            for (int j = 0; j < n0; ++j) {
+                const double2 fv = *at(l0.off_f, j);
+                s.x = fma(__ldg(i0 + (size_t)i * n0 + j), fv.x, s.x);
+                s.y = fma(__ldg(i1 + (size_t)i * n0 + j), fv.y, s.y);
+            }
+            *at(l0.off_u, i) = s;
+        }
+        __syncthreads();
+    }
+    // ---- up: correct, smooth ----
+    for (int l = 1; l <= top; ++l) {
+        const CoarseLevel &lv = a.L[l];
+        const CoarseLevel &lc = a.L[l - 1];
+        for (int i = lane; i < lv.n; i += NL) {  // u -= P u_c
+            const int p1 = __ldg(lv.p_indptr + i + 1);
+            double2 s = zero2;
+            for (int p = __ldg(lv.p_indptr + i); p < p1; ++p) {
+                const double2 xv = *at(lc.off_u, __ldg(lv.p_indices + p));
+                const double w = __ldg(lv.p_vals + p);
+                s.x = fma(w, xv.x, s.x);
+                s.y = fma(w, xv.y, s.y);
+            }
+            double2 uo = *at(lv.off_u, i);
+            uo.x = fma(-1.0, s.x, uo.x);
+            uo.y = fma(-1.0, s.y, uo.y);
+            *at(lv.off_u, i) = uo;
+        }
+        __syncthreads();
+        for (int sw = 0; sw < a.nu; ++sw) sweep(lv, true);
+    }
+    if (valid) {
+        const CoarseLevel &lv = a.L[top];
+        for (int i = lane; i < lv.n; i += NL) stv2(a.u + (size_t)i * a.ld + c, *at(lv.off_u, i));
+    }
+}
+
 }  // namespace stk
 
 using namespace stk;
@@ -152,12 +319,108 @@ struct stk_mg {
     std::vector<Level> L;
     std::unordered_map<GraphKey, GraphEntry, GraphKeyHash> graphs;
     cudaStream_t capture_stream = nullptr;
+    // coarse levels in one launch (k_mg_coarse): -1 = not decided yet, 0 = off
+    int coarse_top = -1;
+    int *coarse_phase_ptr = nullptr;  // device copies of the levels' phase_ptr
+    std::vector<int> coarse_phase_off;
+    size_t coarse_smem = 0;
     ~stk_mg() {
         for (auto &kv : graphs)
             if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
         if (capture_stream) cudaStreamDestroy(capture_stream);
+        if (coarse_phase_ptr) cudaFree(coarse_phase_ptr);
     }
 };
+
+// Decide once which levels the one-launch coarse cycle takes: the largest
+// `top` whose u, f of all levels <= top plus one residual block fit the shared
+// memory of a CTA.  STK_MG_COARSE=0 turns it off.
+static int coarse_setup(stk_mg *mg) {
+    if (mg->coarse_top >= 0) return 0;
+    mg->coarse_top = 0;
+    const char *e = getenv("STK_MG_COARSE");
+    if (e && e[0] == '0') return 0;
+    const size_t budget = 200 * 1024;
+    int top = 0;
+    for (int l = 1; l < mg->nlevels && l < MGC_MAXLV; ++l) {
+        const Level &lv = mg->L[l];
+        if (!lv.sched || !lv.p_indptr || !lv.r_indptr) break;
+        size_t rows = (size_t)lv.n;
+        for (int k = 0; k <= l; ++k) rows += 2 * (size_t)mg->L[k].n;
+        if (rows * MGC_T * sizeof(double) > budget) break;
+        top = l;
+    }
+    if (top < 1) return 0;
+    std::vector<int> host;
+    mg->coarse_phase_off.assign(top + 1, 0);
+    for (int l = 1; l <= top; ++l) {
+        mg->coarse_phase_off[l] = (int)host.size();
+        host.insert(host.end(), mg->L[l].phase_ptr.begin(), mg->L[l].phase_ptr.end());
+    }
+    STK_TRY(check(cudaMalloc(&mg->coarse_phase_ptr, host.size() * sizeof(int)),
+                  "stk_mg: coarse schedule"));
+    STK_TRY(check(cudaMemcpy(mg->coarse_phase_ptr, host.data(), host.size() * sizeof(int),
+                             cudaMemcpyHostToDevice),
+                  "stk_mg: coarse schedule upload"));
+    size_t rows = (size_t)mg->L[top].n;
+    for (int k = 0; k <= top; ++k) rows += 2 * (size_t)mg->L[k].n;
+    mg->coarse_smem = rows * MGC_T * sizeof(double);
+    STK_TRY(check(cudaFuncSetAttribute(k_mg_coarse<true>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)budget),
+                  "stk_mg: coarse kernel attribute"));
+    STK_TRY(check(cudaFuncSetAttribute(k_mg_coarse<false>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)budget),
+                  "stk_mg: coarse kernel attribute"));
+    mg->coarse_top = top;
+    return 0;
+}
+
+// The V-cycle below level l (l <= coarse_top) in one launch.
+static int coarse_cycle(const stk_mg *mg, int l, const int *grp, const double *inv,
+                        const double *f, double *u, int ld, cudaStream_t s, bool zero_guess) {
+    CoarseArgs a;
+    int off = 0;
+    for (int k = 0; k <= l; ++k) {
+        const Level &lv = mg->L[k];
+        CoarseLevel &c = a.L[k];
+        c.n = lv.n;
+        c.nnz = lv.nnz;
+        c.nph = k ? (int)lv.phase_ptr.size() - 1 : 0;
+        c.indptr = lv.indptr;
+        c.indices = lv.indices;
+        c.sched = lv.sched;
+        c.phase_ptr = k ? mg->coarse_phase_ptr + mg->coarse_phase_off[k] : nullptr;
+        c.vals = lv.vals;
+        c.diag = lv.diag;
+        c.p_indptr = lv.p_indptr;
+        c.p_indices = lv.p_indices;
+        c.p_vals = lv.p_vals;
+        c.r_indptr = lv.r_indptr;
+        c.r_indices = lv.r_indices;
+        c.r_vals = lv.r_vals;
+        c.off_u = off;
+        c.off_f = off + lv.n;
+        off += 2 * lv.n;
+    }
+    a.top = l;
+    a.nu = mg->nu;
+    a.off_res = off;
+    a.ld = ld;
+    a.inv = inv;
+    a.grp = grp;
+    a.f = f;
+    a.u_in = zero_guess ? nullptr : u;
+    a.u = u;
+    const size_t smem = (size_t)(off + mg->L[l].n) * MGC_T * sizeof(double);
+    const unsigned grid = (unsigned)((ld + MGC_T - 1) / MGC_T);
+    if (grp)
+        k_mg_coarse<true><<<grid, MGC_NT, smem, s>>>(a);
+    else
+        k_mg_coarse<false><<<grid, MGC_NT, smem, s>>>(a);
+    return check_launch("k_mg_coarse");
+}
 
 static int smooth(const stk_mg *mg, int l, int nsweeps, bool backward, const int *grp,
                   const double *f, double *u, int ld, cudaStream_t s, bool zero_guess = false) {
@@ -212,6 +475,7 @@ static int coarse_solve(const stk_mg *mg, const double *inv, const int *group, c
 // and stands for u = 0 (the reference passes np.zeros, multigrid.py:176,187).
 static int cycle(const stk_mg *mg, int l, const int *grp, const double *inv, const double *f,
                  double *u, int ld, Workspace &ws, cudaStream_t s, bool zero_guess) {
+    if (l >= 1 && l <= mg->coarse_top) return coarse_cycle(mg, l, grp, inv, f, u, ld, s, zero_guess);
     if (l == 0) return coarse_solve(mg, inv, grp, f, u, ld, s);
     const Level &lv = mg->L[l];
     const Level &lc = mg->L[l - 1];
@@ -234,8 +498,15 @@ static int cycle(const stk_mg *mg, int l, const int *grp, const double *inv, con
     // recomputes the fine residuals per coarse row was measured 2.6x slower
     // (6 block passes of DRAM reads instead of ~3): the residual block costs
     // less than the lost locality.
-    STK_TRY(launch_space_spmm_grouped(lv.n, lv.indptr, lv.indices, lv.vals, (size_t)lv.nnz, grp,
-                                      cur, 1.0, -1.0, f, ws.res, ld, s));
+    int rc = 1;
+    if (grp && lv.ktab && lv.kind_of_row && lv.canon_indices)
+        rc = launch_space_spmm_kinds(lv.n, lv.indptr, lv.canon_indices, lv.kind_of_row, lv.ktab,
+                                     mg->G, lv.nkinds, lv.kstride, grp, cur, 1.0, -1.0, f, ws.res,
+                                     ld, s);
+    if (rc == 1)
+        rc = launch_space_spmm_grouped(lv.n, lv.indptr, lv.indices, lv.vals, (size_t)lv.nnz, grp,
+                                       cur, 1.0, -1.0, f, ws.res, ld, s);
+    STK_TRY(rc);
     STK_TRY(launch_space_spmm(lc.n, lv.r_indptr, lv.r_indices, 1, lv.r_vals, nullptr, nullptr,
                               nullptr, ws.res, 1.0, 0.0, nullptr, ws.f[l - 1], ld, s));
     STK_TRY(cycle(mg, l - 1, grp, inv, ws.f[l - 1], ws.u[l - 1], ld, ws, s, true));
@@ -269,6 +540,14 @@ int stk_mg_set_level(stk_mg *mg, int level, int nrows, int nnz, const int *indpt
                      const int *sched_rows, const int *phase_ptr_host, int nphases) {
     if (!mg || level < 0 || level >= mg->nlevels) return fail(-1, "stk_mg_set_level: bad level");
     if (!vals || !diag) return fail(-1, "stk_mg_set_level: values missing");
+    if (mg->coarse_top >= 0) {  // levels change: decide the coarse cycle again
+        if (mg->coarse_phase_ptr) cudaFree(mg->coarse_phase_ptr);
+        mg->coarse_phase_ptr = nullptr;
+        mg->coarse_top = -1;
+        for (auto &kv : mg->graphs)
+            if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+        mg->graphs.clear();
+    }
     Level &lv = mg->L[level];
     lv.n = nrows;
     lv.nnz = nnz;
@@ -308,7 +587,8 @@ int64_t stk_mg_workspace(const stk_mg *mg, int ld) {
 }
 
 int stk_mg_set_fused(stk_mg *mg, int level, const stk_gs_prog *fwd, const stk_gs_prog *bwd,
-                     const double *ktab, int nkinds, int bulk_kind, const double *cvals, int T) {
+                     const double *ktab, int nkinds, int bulk_kind, const double *cvals, int T,
+                     int kstride, const int *kind_of_row, const int *canon_indices) {
     if (!mg || level < 1 || level >= mg->nlevels) return fail(-1, "stk_mg_set_fused: bad level");
     if (T != 8) return fail(-1, "stk_mg_set_fused: T must be 8");
     if (!ktab && !cvals) return fail(-1, "stk_mg_set_fused: values missing");
@@ -320,6 +600,9 @@ int stk_mg_set_fused(stk_mg *mg, int level, const stk_gs_prog *fwd, const stk_gs
     lv.bulk_kind = bulk_kind;
     lv.cvals = cvals;
     lv.fused_T = T;
+    lv.kstride = kstride;
+    lv.kind_of_row = ktab ? kind_of_row : nullptr;
+    lv.canon_indices = ktab ? canon_indices : nullptr;
     for (auto &kv : mg->graphs)  // captured sequences are stale now
         if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     mg->graphs.clear();
@@ -334,6 +617,7 @@ int stk_mg_apply(stk_mg *mg, const int *group, const double *coarse_inv, const d
     if (b == x) return fail(-1, "stk_mg_apply: b must not alias x");
     cudaStream_t s = as_stream(stream);
     const int top = mg->nlevels - 1;
+    STK_TRY(coarse_setup(mg));
     Workspace ws;
     ws.u.resize(mg->nlevels);
     ws.f.resize(mg->nlevels);

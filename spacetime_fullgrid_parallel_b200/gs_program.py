@@ -446,24 +446,49 @@ def compile_program(indptr, indices, wave, nsweeps, backward, capacity,
         if first is None:
             return None
         # more strips / segments: fuller passes of `ngrp` ops, fewer idle SMs
-        # in the last round of CTAs
+        # in the last round of CTAs.  A CTA's run time is its number of steps
+        # and passes, whatever the slab width: on narrow time slabs (few
+        # chunks, e.g. 33 slices per GPU) and on the small levels the SMs are
+        # filled by cutting the level into more items -- shorter pipelines at
+        # the price of recomputed fill columns -- as long as all CTAs still
+        # run in about one round.
         cands = [(first[0], nstrips, 1, first[1])]
-        for ns in range(nstrips, nstrips + (4 if nstrips > 1 else 1)):
-            for nseg in range(1, max_seg + 1):
+        strip_opts = sorted(set(
+            list(range(nstrips, nstrips + (4 if nstrips > 1 else 1))) +
+            [min(vmax, nstrips * k) for k in (2, 3, 4, 6, 8)
+             if nstrips * k * chunks <= 2 * sms]))
+        seg_opts = [g for g in (1, 2, 3, 4, 5, 6, 7, 8, 10) if g <= max(1, ncols // 6)]
+        probes = 0
+        for ns in strip_opts:
+            for nseg in seg_opts:
                 if (ns, nseg) == (nstrips, 1):
                     continue
-                if ns * nseg * chunks > 12 * sms and nseg > 1:
+                ctas = ns * nseg * chunks
+                if ns > nstrips + 3 and ctas > 2 * sms:
+                    break  # extra strips only to fill idle SMs
+                if ctas > 12 * sms and nseg > 1:
                     break
+                if probes >= 64:
+                    break
+                probes += 1
                 got = probe_tiling(ns, nseg)
                 if got is not None:
                     cands.append((got[0], ns, nseg, got[1]))
         cands.sort(key=lambda c: c[:3])
-        for _cost, ns, nseg, its in cands[:3]:
+        for _cost, ns, nseg, its in cands[:16]:
             sched = full_tiling(its)
             if sched is not None:
+                nops_c = sum(len(r['op_row']) for r in sched)
+                if (nops_c / float(n * nsweeps) > max_redundancy
+                        and (ns, nseg) != (nstrips, 1)):
+                    sched = None  # too much recomputation: next candidate
+                    continue
                 tiling = (ns, nseg)
                 nstrips = ns
                 break
+        if sched is None:  # the plain tiling, whatever its redundancy
+            sched = full_tiling(first[1])
+            tiling = (nstrips, 1)
     if sched is None:
         return None
     nops = sum(len(r['op_row']) for r in sched)

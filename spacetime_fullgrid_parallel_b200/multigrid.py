@@ -109,6 +109,15 @@ class FusedLevel:
             assert h.value, 'stk_gs_prog_create failed'
             self.handles.append(h)
         self.device = device
+        # row kinds on the device: the grouped residual SpMM reads the groups'
+        # matrices from the kind table (stk_mg_set_fused)
+        self.d_kind = self.d_cidx = None
+        if self.kind_of_row is not None:
+            self.d_kind = _dev_bytes(np.asarray(self.kind_of_row, dtype=np.int32),
+                                     device, self._keep)
+            self.d_cidx = _dev_bytes(
+                np.asarray(indices, dtype=np.int32)[self.canon], device,
+                self._keep)
         self.ok = True
 
     def values_for(self, group_values):
@@ -152,7 +161,8 @@ class FusedLevel:
         check(lib().stk_mg_set_fused(mg_handle, level, self.handles[0],
                                      self.handles[1], ptr(vals[0]),
                                      self.nkinds, self.bulk_kind, ptr(vals[1]),
-                                     self.T))
+                                     self.T, self.maxnnz + 2, ptr(self.d_kind),
+                                     ptr(self.d_cidx)))
         return True
 
     def __del__(self):

@@ -217,6 +217,7 @@ __global__ void __launch_bounds__(NT, 1) k_gs_fused(const GsArgs a) {
         cp_async_commit();
     }
     int fr = 0;  // f ring slot of the current pass
+    unsigned rr = 0, rpar = 0;  // record ring slot of the current pass and its phase parity
 
     auto issue_load = [&](const int2 &e) {
         double *dst = win + (unsigned)e.y * T + woff;
@@ -252,9 +253,10 @@ __global__ void __launch_bounds__(NT, 1) k_gs_fused(const GsArgs a) {
         if (p == info.x) cp_async_commit();  // no pass in this step: its own group
         // 2. the passes of this step (window loads join the first pass's group)
         for (; p < info.x; ++p) {
-            const int q = p - p0, r = q & (GS_RING - 1);
-            mbar_wait(mbar + r, (unsigned)(q / GS_RING) & 1u);
-            const uint4 *slot = ring + r * pass_q + grp;
+            mbar_wait(mbar + rr, rpar);
+            const uint4 *slot = ring + rr * pass_q + grp;
+            rr = (rr + 1) & (GS_RING - 1);
+            rpar ^= (rr == 0);
             const uint4 h = slot[0];
             uint4 nb = slot[NGRP];
             cp_async_wait<GS_FRING - 1>();  // this pass's f has landed (own copy)

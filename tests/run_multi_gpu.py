@@ -86,6 +86,20 @@ def main():
             print('case %s (%s) on %d GPUs: iters %d (ref %d), worst apply '
                   'err %.2e' % (tag, mode, size, iters, ref_iters, worst),
                   flush=True)
+    # precond='direct' (heateq_mpi.py:154-157) on the live communicator
+    gd = np.load(os.path.join(ROOT, 'tests', 'golden', 'direct.npz'))
+    tag = 'direct_Jt3_Js3_composite_P2'
+    if size <= 9:
+        heq = HeatEquationMPI(J_space=3, J_time=3, precond='direct', comm=comm)
+        a, b = heq.dofs_distr.t_begin, heq.dofs_distr.t_end
+        x = KronVectorMPI(heq.dofs_distr, rand((heq.N, heq.M))[a:b])
+        for name in ('S', 'P', 'WT_S_W'):
+            err = rel((getattr(heq, name) @ x).X_loc, gd['%s__%s' % (tag, name)][a:b])
+            assert err < 1e-12, (tag, name, err, rank)
+        w, iters = PCG(heq.WT_S_W, heq.P, heq.rhs)
+        assert abs(iters - int(gd[tag + '__iters'])) <= 1, (tag, iters)
+        if rank == 0:
+            print('case %s on %d GPUs: iters %d' % (tag, size, iters), flush=True)
     torch.cuda.synchronize()
     comm.Barrier()
     if rank == 0:

@@ -191,6 +191,12 @@ def init_from_env(backend=None):
         if torch.cuda.is_available():
             torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        # The exchanges of this path are point-to-point batches between a few
+        # peers (halo slices to the two neighbours, wavelet boundary slices to
+        # <= 7 ranks), 8-130 MB per peer.  NCCL's default gives a peer pair few
+        # channels (measured 60-160 GB/s of the 770 GB/s a B200 pair can move);
+        # more channels per peer let one pair use the NVLink bandwidth.
+        os.environ.setdefault('NCCL_MIN_P2P_NCHANNELS', '16')
         dist.init_process_group(backend=backend)
     elif torch.cuda.is_available():
         torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))

@@ -100,20 +100,25 @@ __global__ void k_wavelet_lift(int M, int J, const double *src, double *x, int l
 // owns plus the <= 2J-1 remote slices its rows depend on): about
 // a third of the multiply-adds of the fused matrix, and the adjoint chain
 // delivers the partial sums for the remote slices (yh_out) in the same pass.
-// Shared layout: tval[NNZ] | per warp: A[n_ext], scratch[n_ext] | ints.
+// Shared layout: tval[NNZ] | A[RT][n_ext] | per warp scratch[n_ext] | ints.
+// A CTA takes tiles of RT (32 when it fits) space dofs: the halo slices are slice-major
+// (n_halo x M, as the exchange delivers them), so reading -- and, for the
+// adjoint, writing -- them for 32 consecutive dofs at a time makes those
+// accesses 256-byte runs instead of one 32-byte sector per value.
 __global__ void __launch_bounds__(256)
-    k_time_chain(int M, int n_loc, int n_halo, int nlev, const int *__restrict__ lev_ptr,
+    k_time_chain(const int CHAIN_RT, int M, int n_loc, int n_halo, int nlev, const int *__restrict__ lev_ptr,
                  const int *__restrict__ trow, const int *__restrict__ tptr,
                  const int *__restrict__ tcol, const double *__restrict__ tval, int R, int NNZ,
                  const double *__restrict__ x, int ldx, const double *__restrict__ xh,
                  double *__restrict__ y, int ldy, double *__restrict__ yh_out) {
     extern __shared__ double smem[];
     const int n_ext = n_loc + n_halo;
+    const int pe = n_ext | 1;  // odd row pitch: the tile's rows fall into different banks
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     double *s_val = smem;
-    double *A = s_val + NNZ + (size_t)warp * 2 * n_ext;
-    double *B = A + n_ext;
-    int *s_lev = reinterpret_cast<int *>(s_val + NNZ + (size_t)wpb * 2 * n_ext);
+    double *At = s_val + NNZ;                          // [CHAIN_RT][pe]
+    double *B = At + (size_t)CHAIN_RT * pe + (size_t)warp * n_ext;
+    int *s_lev = reinterpret_cast<int *>(At + (size_t)CHAIN_RT * pe + (size_t)wpb * n_ext);
     int *s_row = s_lev + nlev + 1;
     int *s_ptr = s_row + R;
     int *s_col = s_ptr + R + 1;
@@ -124,29 +129,45 @@ __global__ void __launch_bounds__(256)
     for (int k = threadIdx.x; k < R; k += blockDim.x) s_row[k] = __ldg(trow + k);
     for (int k = threadIdx.x; k <= R; k += blockDim.x) s_ptr[k] = __ldg(tptr + k);
     for (int k = threadIdx.x; k <= nlev; k += blockDim.x) s_lev[k] = __ldg(lev_ptr + k);
-    __syncthreads();
-    for (int i = blockIdx.x * wpb + warp; i < M; i += gridDim.x * wpb) {
-        const double *xi = x + (size_t)i * ldx;
-        for (int t = lane; t < n_loc; t += 32) A[t] = xi[t];
-        for (int h = lane; h < n_halo; h += 32)
-            A[n_loc + h] = xh ? __ldg(xh + (size_t)h * M + i) : 0.0;
-        __syncwarp();
-        for (int lev = 0; lev < nlev; ++lev) {
-            const int q0 = s_lev[lev], q1 = s_lev[lev + 1];
-            for (int q = q0 + lane; q < q1; q += 32) {
-                double acc = 0.0;
-                for (int p = s_ptr[q]; p < s_ptr[q + 1]; ++p) acc = fma(s_val[p], A[s_col[p]], acc);
-                B[q - q0] = acc;
-            }
-            __syncwarp();
-            for (int q = q0 + lane; q < q1; q += 32) A[s_row[q]] = B[q - q0];
-            __syncwarp();
+    const int ntiles = (M + CHAIN_RT - 1) / CHAIN_RT;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int i0 = tile * CHAIN_RT;
+        const int rt = min(CHAIN_RT, M - i0);
+        __syncthreads();  // tables staged / previous tile stored
+        for (int r = warp; r < rt; r += wpb) {  // local slices: one contiguous run per dof
+            const double *xi = x + (size_t)(i0 + r) * ldx;
+            for (int t = lane; t < n_loc; t += 32) At[r * pe + t] = xi[t];
         }
-        double *yi = y + (size_t)i * ldy;
-        for (int t = lane; t < ldy; t += 32) yi[t] = t < n_loc ? A[t] : 0.0;
-        if (yh_out)
-            for (int h = lane; h < n_halo; h += 32) yh_out[(size_t)h * M + i] = A[n_loc + h];
-        __syncwarp();
+        for (int e = threadIdx.x; e < n_halo * CHAIN_RT; e += blockDim.x) {
+            const int h = e / CHAIN_RT, r = e - h * CHAIN_RT;
+            if (r < rt)
+                At[r * pe + n_loc + h] = xh ? __ldg(xh + (size_t)h * M + i0 + r) : 0.0;
+        }
+        __syncthreads();
+        for (int r = warp; r < rt; r += wpb) {
+            double *A = At + r * pe;
+            for (int lev = 0; lev < nlev; ++lev) {
+                const int q0 = s_lev[lev], q1 = s_lev[lev + 1];
+                for (int q = q0 + lane; q < q1; q += 32) {
+                    double acc = 0.0;
+                    for (int p = s_ptr[q]; p < s_ptr[q + 1]; ++p)
+                        acc = fma(s_val[p], A[s_col[p]], acc);
+                    B[q - q0] = acc;
+                }
+                __syncwarp();
+                for (int q = q0 + lane; q < q1; q += 32) A[s_row[q]] = B[q - q0];
+                __syncwarp();
+            }
+            double *yi = y + (size_t)(i0 + r) * ldy;
+            for (int t = lane; t < ldy; t += 32) yi[t] = t < n_loc ? A[t] : 0.0;
+        }
+        if (yh_out) {
+            __syncthreads();
+            for (int e = threadIdx.x; e < n_halo * CHAIN_RT; e += blockDim.x) {
+                const int h = e / CHAIN_RT, r = e - h * CHAIN_RT;
+                if (r < rt) yh_out[(size_t)h * M + i0 + r] = At[r * pe + n_loc + h];
+            }
+        }
     }
 }
 
@@ -163,23 +184,25 @@ extern "C" int stk_time_chain(int M, int n_loc, int n_halo, int nlev, const int 
     if (n_loc > ldy || n_loc > ldx) return fail(-1, "stk_time_chain: n_loc exceeds a pitch");
     if (M == 0) return 0;
     const int n_ext = n_loc + n_halo;
+    const int wpb = 8;
     const size_t mat = (size_t)NNZ * 12 + (size_t)(2 * R + nlev + 2) * 4 + 16;
-    const size_t per_warp = (size_t)2 * n_ext * 8;
-    int wpb = 8;
-    while (wpb > 1 && mat + wpb * per_warp > 200 * 1024) wpb >>= 1;
-    if (mat + wpb * per_warp > 200 * 1024)
-        return fail(-1, "stk_time_chain: chain does not fit shared memory");
-    const size_t smem = mat + wpb * per_warp;
+    int CHAIN_RT = 32;  // dofs per tile: as many as fit (long time slabs: fewer)
+    auto need = [&](int rt) {
+        return mat + sizeof(double) * ((size_t)rt * (n_ext | 1) + (size_t)wpb * n_ext);
+    };
+    while (CHAIN_RT > 1 && need(CHAIN_RT) > 200 * 1024) CHAIN_RT >>= 1;
+    const size_t smem = need(CHAIN_RT);
+    if (smem > 200 * 1024) return fail(-1, "stk_time_chain: chain does not fit shared memory");
     int ctas = (int)((220 * 1024) / (smem + 1024));
     if (ctas > 6) ctas = 6;
     if (ctas < 1) ctas = 1;
     cudaError_t e = cudaFuncSetAttribute(k_time_chain, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          200 * 1024);
     if (e != cudaSuccess) return check(e, "stk_time_chain: smem attribute");
-    int64_t want = ((int64_t)M + wpb - 1) / wpb;
+    int64_t want = ((int64_t)M + CHAIN_RT - 1) / CHAIN_RT;
     int64_t cap = (int64_t)sm_count() * ctas;
     k_time_chain<<<(unsigned)(want < cap ? want : cap), wpb * 32, smem, as_stream(stream)>>>(
-        M, n_loc, n_halo, nlev, lev_ptr, trow, tptr, tcol, tval, R, NNZ, x, ldx, xh, y, ldy,
+        CHAIN_RT, M, n_loc, n_halo, nlev, lev_ptr, trow, tptr, tcol, tval, R, NNZ, x, ldx, xh, y, ldy,
         yh_out);
     return check_launch("k_time_chain");
 }

@@ -108,7 +108,7 @@ def main():
         torch.cuda.synchronize()
 
     mk = lambda: [torch.cuda.Event(enable_timing=True) for _ in range(len(phases) + 1)]
-    for _ in range(2):  # warm-up: graphs captured, NCCL connections up
+    for _ in range(4):  # warm-up: graphs captured, NCCL connections up
         run_once(mk())
     barrier()
     acc = np.zeros(len(phases))

@@ -87,6 +87,7 @@ class TorchComm:
         self.dist, self.group = dist, group
         self.rank = dist.get_rank(group)
         self.size = dist.get_world_size(group)
+        self._peer = None
 
     def Get_rank(self):
         return self.rank
@@ -135,6 +136,11 @@ class TorchComm:
         work already enqueued on the current stream; what the caller enqueues
         before `exchange_end` overlaps them (the `callback` of
         mpi_vector.py:155-183)."""
+        if peer_copy_enabled() and all(t.is_cuda for t in list(sends.values()) +
+                                       list(recvs.values())):
+            if self._peer is None:
+                self._peer = PeerWindows(self)
+            return self._peer.exchange_begin(sends, recvs)
         ops = []
         for peer in sorted(recvs):
             ops.append(self.dist.P2POp(self.dist.irecv, recvs[peer], peer,
@@ -151,6 +157,7 @@ class TorchComm:
         for req in reqs:
             req.wait()
 
+
     def all_to_all(self, send_chunks, recv_chunks):
         """send_chunks[p] goes to rank p, recv_chunks[p] comes from rank p."""
         if send_chunks[0].is_cuda:
@@ -161,6 +168,115 @@ class TorchComm:
             self.exchange(
                 {p: send_chunks[p] for p in range(self.size) if p != me},
                 {p: recv_chunks[p] for p in range(self.size) if p != me})
+
+
+
+def peer_copy_enabled():
+    import os
+    return os.environ.get('STK_PEER_COPY', '0') == '1'
+
+
+class _StreamEvent:
+    """`wait()` makes the current stream wait for an event of the transfer
+    stream (the request protocol of exchange_end)."""
+    def __init__(self, event):
+        self.event = event
+
+    def wait(self):
+        torch.cuda.current_stream().wait_event(self.event)
+
+
+class PeerWindows:
+    """Point-to-point batches as peer-to-peer copies over NVLink: every rank
+    owns two send windows in HBM that the other ranks of the box map through
+    CUDA IPC; an exchange packs into the window, one scalar allreduce tells
+    everyone that all windows are written, and each rank pulls its pieces from
+    its peers' windows with device-to-device copies (copy engines, no SMs, no
+    staging through NCCL's channel buffers).  The windows alternate, so the
+    allreduce of the next exchange also guards the reuse.  Everything runs on a
+    side stream; `exchange_end` makes the caller's stream wait for it.
+
+    Needs all ranks on one node with every GPU visible to every process (what
+    torchrun gives).  The pieces' offsets inside the senders' windows are
+    agreed on once per exchange pattern (an object all-gather)."""
+    def __init__(self, comm):
+        self.comm = comm
+        self.stream = torch.cuda.Stream()
+        self.capacity = 0
+        self.windows = None      # my two windows (uint8)
+        self.peer = None         # peer[p][k]: rank p's window k as seen from here
+        self.layouts = {}
+        self.count = 0
+        self.flag = torch.zeros(1, dtype=torch.float32, device='cuda')
+
+    def _ensure(self, nbytes):
+        import torch.distributed as dist
+        from torch.multiprocessing.reductions import reduce_tensor
+        need = torch.tensor([nbytes], dtype=torch.int64, device='cuda')
+        dist.all_reduce(need, op=dist.ReduceOp.MAX, group=self.comm.group)
+        need = int(need.item())
+        if need <= self.capacity:
+            return
+        torch.cuda.synchronize()
+        self.peer = None
+        self.capacity = int(need * 1.25) + 4096
+        self.windows = [torch.empty(self.capacity, dtype=torch.uint8, device='cuda')
+                        for _ in range(2)]
+        mine = [reduce_tensor(w) for w in self.windows]
+        everyone = [None] * self.comm.size
+        dist.all_gather_object(everyone, mine, group=self.comm.group)
+        self.peer = []
+        for p, handles in enumerate(everyone):
+            if p == self.comm.rank:
+                self.peer.append(self.windows)
+            else:
+                self.peer.append([fn(*args) for fn, args in handles])
+        self.count = 0
+
+    def exchange_begin(self, sends, recvs):
+        import torch.distributed as dist
+        key = (tuple(sorted((p, t.numel() * t.element_size()) for p, t in sends.items())),
+               tuple(sorted((p, t.numel() * t.element_size()) for p, t in recvs.items())))
+        if key not in self.layouts:
+            # offsets of my pieces in my window, 256-byte aligned; every rank
+            # learns where its pieces sit in its peers' windows
+            off, mine = 0, {}
+            for p in sorted(sends):
+                n = sends[p].numel() * sends[p].element_size()
+                mine[p] = (off, n)
+                off += (n + 255) // 256 * 256
+            table = [None] * self.comm.size
+            dist.all_gather_object(table, mine, group=self.comm.group)
+            self._ensure(off)
+            src = {}
+            for p in recvs:
+                o, n = table[p][self.comm.rank]
+                assert n == recvs[p].numel() * recvs[p].element_size()
+                src[p] = o
+            self.layouts[key] = (mine, src)
+        mine, src = self.layouts[key]
+        k = self.count & 1
+        self.count += 1
+        cur = torch.cuda.current_stream()
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            win = self.windows[k]
+            for p, t in sends.items():
+                o, n = mine[p]
+                win[o:o + n].view(t.dtype).view(t.shape).copy_(t)
+            # all windows written (and the previous use of the other window read)
+            dist.all_reduce(self.flag, op=dist.ReduceOp.MAX, group=self.comm.group)
+            for p, t in recvs.items():
+                n = t.numel() * t.element_size()
+                t.copy_(self.peer[p][k][src[p]:src[p] + n].view(t.dtype).view(t.shape),
+                        non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self.stream)
+        for t in list(sends.values()) + list(recvs.values()):
+            t.record_stream(self.stream)
+        self.comm.bytes_sent = getattr(self.comm, 'bytes_sent', 0) + sum(
+            t.numel() * t.element_size() for t in sends.values())
+        return [_StreamEvent(done)]
 
 
 _world = None

@@ -133,3 +133,31 @@ def test_deep_wavefront_numbering_is_rejected():
     assert depth > 8
     assert gp.compile_program(A.indptr, A.indices, wave, 3, False,
                               3000) is None
+
+
+def test_narrow_slabs_get_more_items():
+    """A CTA's run time is its number of steps and passes whatever the slab
+    width, so with few time chunks per item the compiler cuts the level into
+    more items (shorter pipelines) until one round of CTAs fills the SMs -- and
+    the program still reproduces the sequential sweeps."""
+    A = _square_level(6)
+    n = A.shape[0]
+    wave, _ = gp.wavefronts(A.indptr, A.indices)
+    progs = {}
+    for chunks in (33, 5):
+        progs[chunks] = gp.compile_program(A.indptr, A.indices, wave, 3, False,
+                                           2300, chunks=chunks, sms=148)
+        assert progs[chunks] is not None
+
+    def longest(pg):
+        return int((np.diff(pg.item_pass) + np.diff(pg.item_step) // 2).max())
+
+    assert progs[5].nitems > progs[33].nitems
+    assert longest(progs[5]) < longest(progs[33])
+    assert progs[5].stats['redundancy'] <= 1.7
+    rng = np.random.RandomState(4)
+    f, u0 = rng.rand(n, 2), rng.rand(n, 2)
+    out = emulate(progs[5], A.indptr, A.data, A.diagonal(), f, u0,
+                  indices=A.indices)
+    ref = _seq(A, f, u0, 3, False)
+    assert np.abs(out - ref).max() <= 1e-13 * np.abs(ref).max()

@@ -329,3 +329,22 @@ def test_chained_wavelet_all_ranks_with_exchange():
                 out_wt[bounds[p][0] + plans[p].send_to[r]] += packed[r][off:off + cnt]
         assert np.abs(out_w - W @ X).max() < 1e-12, (J, P)
         assert np.abs(out_wt - W.T @ X).max() < 1e-12, (J, P)
+
+
+def test_locality_order_is_a_local_walk():
+    """Row schedule of the SpMM kernels (stk_csr_set_row_order): a permutation
+    of the rows in which the neighbours of a row are visited close to it, where
+    the hierarchical numbering scatters them over the whole index range."""
+    from spacetime_fullgrid_parallel_b200.linop import locality_order
+    prob = SquareProblem(6, 1)
+    A = prob.A_x.tocsr()
+    n = A.shape[0]
+    order = locality_order(A)
+    assert sorted(order.tolist()) == list(range(n))
+    pos = np.empty(n, dtype=np.int64)
+    pos[order] = np.arange(n)
+    rows = np.repeat(np.arange(n), np.diff(A.indptr))
+    walk = np.abs(pos[rows] - pos[A.indices]).max()
+    index = np.abs(rows - A.indices).max()
+    assert walk <= 2 * int(np.sqrt(n)) and index > 10 * walk
+    assert locality_order(prob.hierarchy.P_mats[-1]) is None  # not square

@@ -315,22 +315,30 @@ class InvLinOp:
 
 class KronLinOp:
     """Serial (mat_time (x) mat_space) x on a host vector of N*M entries
-    (linop.py:6-15), computed on the device."""
+    (linop.py:6-15), computed on the device.  `mat_time` is any square sparse
+    time matrix or an operator with `.as_matrix()` (the wavelet transform); the
+    reference's rectangular factors have no use on this path and are refused."""
     def __init__(self, mat_time, mat_space):
-        self.mat_time = sp.csr_matrix(mat_time)
+        if hasattr(mat_time, 'as_matrix'):
+            mat_time = mat_time.as_matrix()
+        self.mat_time = sp.csr_matrix(mat_time, dtype=np.float64)
         self.mat_space = as_space_op(mat_space)
+        if (self.mat_time.shape[0] != self.mat_time.shape[1]
+                or self.mat_space.shape[0] != self.mat_space.shape[1]):
+            raise ValueError('KronLinOp: square factors only on the device path')
         self.N, self.M = self.mat_time.shape[0], self.mat_space.shape[0]
         self.shape = (self.N * self.M, self.N * self.M)
 
     def __matmul__(self, x):
         from .comm import SerialComm
-        from .mpi_kron import TridiagKronMatMPI
+        from .mpi_kron import IdentityKronMatMPI, SparseKronIdentityMPI
         from .mpi_vector import DofDistributionMPI, KronVectorMPI
         d = DofDistributionMPI(SerialComm(), self.N, self.M)
-        op = TridiagKronMatMPI(d, self.mat_time, self.mat_space)
         v = KronVectorMPI(d, np.asarray(x, dtype=np.float64).reshape(
             self.N, self.M))
-        return (op @ v).to_host().reshape(-1)
+        out = SparseKronIdentityMPI(d, self.mat_time) @ v
+        IdentityKronMatMPI(d, self.mat_space)._matvec(out, out)  # alias-safe
+        return out.to_host().reshape(-1)
 
 
 def host_apply(op, B):

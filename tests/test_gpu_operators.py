@@ -282,6 +282,10 @@ def test_serial_glue_and_shared_matrices(cuda):
     x = rand((35, ), seed=3)
     assert rel(KronLinOp(T, A.tocsr()) @ x,
                np.kron(T.toarray(), A.toarray()) @ x) < TOL
+    # any sparse time factor, not only tridiagonal ones (linop.py:6-15)
+    Wt = WaveletTransformOp(2, interleaved=True)
+    assert rel(KronLinOp(Wt, A.tocsr()) @ x,
+               np.kron(Wt.as_matrix().toarray(), A.toarray()) @ x) < TOL
     dA = shared_sparse_matrix(A.tocsr())
     assert dA.shape == (7, 7) and rel(dA @ np.eye(7), A.toarray()) < 1e-15
     comp = CompositeLinOp([dA, B.tocsr(), dA])

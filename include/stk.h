@@ -285,6 +285,14 @@ int stk_mg_set_fused(stk_mg *mg, int level, const stk_gs_prog *fwd,
  * order, device arrays, may be NULL) also serve the level's grouped residual
  * A_{g(t)} u - f (multigrid.py:174): the G matrices are read from the table in
  * shared memory instead of G value arrays in HBM. */
+/* A second pair of programs of the same level, compiled for wide blocks (a
+ * CTA's run time does not depend on the slab width, so the best tiling does:
+ * few long items when there are many time chunks, many short ones when there
+ * are few): stk_mg_apply uses it for blocks of at least min_chunks chunks of T
+ * time slices -- the two brackets of the Schur operator side by side
+ * (heateq_mpi.py:166-178) -- and the first pair below that. */
+int stk_mg_set_fused_wide(stk_mg *mg, int level, const stk_gs_prog *fwd,
+                          const stk_gs_prog *bwd, int min_chunks);
 /* HOST helper (host pointers): interval colouring of window lifetimes
  * [start[q], end[q]] (macro-steps); slot[q] out; returns the slots used. */
 int stk_gs_alloc_slots(int n, const int *start, const int *end, int *slot);

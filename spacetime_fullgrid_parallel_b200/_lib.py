@@ -78,6 +78,7 @@ SIGNATURES = {
     'stk_gs_prog_destroy': (None, [_vp]),
     'stk_mg_set_fused': (_int, [_vp, _int, _vp, _vp, _vp, _int, _int, _vp,
                                 _int, _int, _vp, _vp]),
+    'stk_mg_set_fused_wide': (_int, [_vp, _int, _vp, _vp, _int]),
     'stk_gs_fused': (_int, [
         _vp, _int, _int, _vp, _int, _int, _vp, _i64, _vp, _vp, _vp, _vp, _int,
         _vp

@@ -56,6 +56,10 @@ struct Level {
     // fused smoother (stk_gsfused.cu): nu forward / nu backward sweeps as one
     // launch each, out of place; null = per-wavefront launches
     const stk_gs_prog *fused_fwd = nullptr, *fused_bwd = nullptr;
+    // a second pair of programs, tiled for wide blocks (the two brackets of the
+    // Schur operator side by side): used from `wide_min_chunks` time chunks on
+    const stk_gs_prog *wide_fwd = nullptr, *wide_bwd = nullptr;
+    int wide_min_chunks = 0;
     const double *ktab = nullptr;   // [G][nkinds][maxnnz + 2] (programs with kinds)
     const double *cvals = nullptr;  // [G][nnz], program entry order (generic programs)
     int nkinds = 0, bulk_kind = -1, fused_T = 8, kstride = 0;
@@ -459,7 +463,11 @@ struct Workspace {
 static int smooth_fused(const stk_mg *mg, int l, bool backward, const int *grp, const double *f,
                         const double *uin, double *uout, int ld, cudaStream_t s) {
     const Level &lv = mg->L[l];
-    return gs_fused_run(backward ? lv.fused_bwd : lv.fused_fwd, mg->G, lv.fused_T, lv.ktab,
+    const bool wide = lv.wide_fwd && lv.wide_bwd &&
+                      (ld + lv.fused_T - 1) / lv.fused_T >= lv.wide_min_chunks;
+    const stk_gs_prog *pg = backward ? (wide ? lv.wide_bwd : lv.fused_bwd)
+                                     : (wide ? lv.wide_fwd : lv.fused_fwd);
+    return gs_fused_run(pg, mg->G, lv.fused_T, lv.ktab,
                         lv.nkinds, lv.bulk_kind, lv.cvals, (size_t)lv.nnz, grp, f, uin, uout, ld,
                         s);
 }
@@ -604,6 +612,22 @@ int stk_mg_set_fused(stk_mg *mg, int level, const stk_gs_prog *fwd, const stk_gs
     lv.kind_of_row = ktab ? kind_of_row : nullptr;
     lv.canon_indices = ktab ? canon_indices : nullptr;
     for (auto &kv : mg->graphs)  // captured sequences are stale now
+        if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    mg->graphs.clear();
+    return 0;
+}
+
+int stk_mg_set_fused_wide(stk_mg *mg, int level, const stk_gs_prog *fwd, const stk_gs_prog *bwd,
+                          int min_chunks) {
+    if (!mg || level < 1 || level >= mg->nlevels)
+        return fail(-1, "stk_mg_set_fused_wide: bad level");
+    Level &lv = mg->L[level];
+    if (!lv.fused_fwd || !lv.fused_bwd)
+        return fail(-1, "stk_mg_set_fused_wide: attach the level's programs first");
+    lv.wide_fwd = fwd;
+    lv.wide_bwd = bwd;
+    lv.wide_min_chunks = min_chunks;
+    for (auto &kv : mg->graphs)
         if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     mg->graphs.clear();
     return 0;

@@ -54,9 +54,10 @@ class FusedLevel:
     set of group matrices on that pattern can run them (`values_for`)."""
     def __init__(self, indptr, indices, wave, nsweeps, base_values, device,
                  chunks=33, sms=148, T=None, generic=False, capacity=None,
-                 ngrp=None):
+                 ngrp=None, chunks_wide=None):
         self.ok = False
         self.handles = []
+        self.handles_wide, self.programs_wide, self.wide_min_chunks = [], [], 0
         self._keep = []
         self.T = T = FUSED_T if T is None else T
         self.indptr = np.asarray(indptr, dtype=np.int64)
@@ -99,7 +100,27 @@ class FusedLevel:
                 return
             progs.append(pg)
         self.programs = progs
-        for pg in progs:
+        # The same level tiled for blocks twice as wide (the Schur operator
+        # solves for both of its brackets in one block): with more time chunks
+        # per item, fewer and longer items are better.  Kept only if the
+        # compiler indeed chooses another tiling.
+        if chunks_wide and chunks_wide > chunks and os.environ.get(
+                'STK_GS_WIDE', '1') != '0':
+            wide = []
+            for backward in (False, True):
+                pg = gs_program.compile_program(
+                    indptr, indices, wave, nsweeps, backward, capacity,
+                    embedding=emb, kind_of_row=self.kind_of_row,
+                    canon=self.canon, chunks=chunks_wide, sms=sms, ngrp=ngrp,
+                    tiling=wide[0].tiling if wide else None)
+                if pg is None or pg.tiling == progs[0].tiling:
+                    wide = []
+                    break
+                wide.append(pg)
+            self.programs_wide = wide
+            self.wide_min_chunks = (chunks + chunks_wide + 1) // 2
+
+        def upload(pg):
             d = [_dev_bytes(x, device, self._keep)
                  for x in (pg.item_step, pg.item_pass, pg.step_info, pg.op,
                            pg.ld)]
@@ -107,7 +128,10 @@ class FusedLevel:
                 pg.nitems, pg.nslots, pg.maxnnz, int(pg.generic), pg.recw,
                 pg.ngrp, *[ptr(t) for t in d]))
             assert h.value, 'stk_gs_prog_create failed'
-            self.handles.append(h)
+            return h
+
+        self.handles = [upload(pg) for pg in progs]
+        self.handles_wide = [upload(pg) for pg in self.programs_wide]
         self.device = device
         # row kinds on the device: the grouped residual SpMM reads the groups'
         # matrices from the kind table (stk_mg_set_fused)
@@ -163,13 +187,18 @@ class FusedLevel:
                                      self.nkinds, self.bulk_kind, ptr(vals[1]),
                                      self.T, self.maxnnz + 2, ptr(self.d_kind),
                                      ptr(self.d_cidx)))
+        if self.handles_wide:
+            check(lib().stk_mg_set_fused_wide(mg_handle, level,
+                                              self.handles_wide[0],
+                                              self.handles_wide[1],
+                                              self.wide_min_chunks))
         return True
 
     def __del__(self):
         try:
-            for h in self.handles:
+            for h in self.handles + self.handles_wide:
                 lib().stk_gs_prog_destroy(h)
-            self.handles = []
+            self.handles, self.handles_wide = [], []
         except Exception:
             pass
 
@@ -324,6 +353,7 @@ class MultiGridFamily:
                 chunks = -(-(ld_hint or 256) // FUSED_T)
                 fused = FusedLevel(pat.indptr, pat.indices, wave, smoothsteps,
                                    base_vals, dev, chunks=chunks,
+                                   chunks_wide=-(-2 * (ld_hint or 256) // FUSED_T),
                                    sms=torch.cuda.get_device_properties(
                                        dev).multi_processor_count)
                 if not fused.ok:

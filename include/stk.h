@@ -141,6 +141,21 @@ int stk_time_apply2(int M, int nrows_t, const int *indptr, const int *indices,
                     int ldx, int ncols_local, const double *xh0, int n_halo0,
                     const double *xh1, double alpha, double beta, double *y,
                     int ldy, int wy, void *stream);
+/* Both brackets of the regrouped Schur operator for TRIDIAGONAL time matrices
+ * in one pass (the four TridiagKronIdentityMPI applies of heateq_mpi.py:166-178,
+ * mpi_kron.py:186-201):
+ *   y1 = (Ta (x) I) x0 + (Tb (x) I) x1,   y2 = (Tc (x) I) x0 + (Td (x) I) x1.
+ * coef: 12 arrays of ld doubles (device): for local time row t the multipliers
+ * of x0[t-1], x0[t], x0[t+1], x1[t-1], x1[t], x1[t+1] in y1[t], then the same
+ * six for y2[t]; zero for t >= n and for neighbours that do not exist.
+ * prev / next: the boundary slices of the neighbour ranks (M doubles each,
+ * mpi_vector.py:140-187) or NULL.  x0, x1 have pitch ldx, y1, y2 pitch ldy; ld
+ * columns are written (pads as zero). */
+int stk_time_tridiag_pair(int M, int n, int ld, const double *coef,
+                          const double *x0, const double *x1, int ldx,
+                          const double *prev0, const double *next0,
+                          const double *prev1, const double *next1, double *y1,
+                          double *y2, int ldy, void *stream);
 /* Two matrices on one sparsity pattern (M_x and A_x, heateq_mpi.py:166-178):
  * split: y0 = A0 x, y1 = A1 x (x and the pattern read once);
  * pair : y = alpha * (A0 x0 + A1 x1) + beta * z  (x0, x1 of pitch ldx). */

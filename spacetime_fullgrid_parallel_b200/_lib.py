@@ -43,6 +43,10 @@ SIGNATURES = {
         _int, _int, _vp, _vp, _vp, _vp, _vp, _int, _int, _vp, _int, _vp, _dbl,
         _dbl, _vp, _int, _int, _vp
     ]),
+    'stk_time_tridiag_pair': (_int, [
+        _int, _int, _int, _vp, _vp, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp,
+        _int, _vp
+    ]),
     'stk_space_spmm_split': (_int, [
         _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _vp
     ]),

@@ -306,6 +306,71 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// Both brackets of the regrouped Schur operator in one pass
+// (heateq_mpi.py:166-178):
+//     y1 = (Ta (x) I) x0 + (Tb (x) I) x1,     y2 = (Tc (x) I) x0 + (Td (x) I) x1
+// for four TRIDIAGONAL time matrices (A_t, L_t, L_t^T, M_t).  A thread owns one
+// pair of adjacent time values for the whole kernel, so its 24 stencil
+// coefficients live in registers and a CTA walks the space dofs: per dof a
+// thread loads one double2 of x0 and of x1, gets the two neighbouring values
+// from the adjacent lanes (shuffles; warp edges re-read them), and stores one
+// double2 of each result: 32 B per dof of traffic and no matrix loads at all,
+// where two passes of the general k_time_apply2 move 48 B and are bound by the
+// L1 data path (18 broadcast loads of CSR entries per output).
+// coef[k][t], k = 0..11: multipliers of x0[t-1], x0[t], x0[t+1], x1[t-1],
+// x1[t], x1[t+1] for y1[t], then the same for y2[t]; zero for t >= n and for
+// neighbours that do not exist.  prev/next: the neighbour ranks' boundary
+// slices (M doubles each) or NULL.
+template <int NT>
+__global__ void __launch_bounds__(NT)
+    k_time_tridiag_pair(int M, int n, int ld2, const double *__restrict__ coef, int ldc,
+                        const double *__restrict__ x0, const double *__restrict__ x1, int ldx,
+                        const double *__restrict__ prev0, const double *__restrict__ next0,
+                        const double *__restrict__ prev1, const double *__restrict__ next1,
+                        double *__restrict__ y1, double *__restrict__ y2, int ldy) {
+    const int cp = threadIdx.x, lane = threadIdx.x & 31;
+    const bool live = cp < ld2;
+    const int t = 2 * cp;
+    double2 c[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k)
+        c[k] = live ? ldg2(coef + (size_t)k * ldc + t) : make_double2(0.0, 0.0);
+    for (int i = blockIdx.x; i < M; i += gridDim.x) {
+        const double *r0 = x0 + (size_t)i * ldx, *r1 = x1 + (size_t)i * ldx;
+        double2 a = live ? ldv2(r0 + t) : make_double2(0.0, 0.0);
+        double2 b = live ? ldv2(r1 + t) : make_double2(0.0, 0.0);
+        if (t + 1 == n) {  // the slice after the last local one is the neighbour's
+            a.y = next0 ? __ldg(next0 + i) : 0.0;
+            b.y = next1 ? __ldg(next1 + i) : 0.0;
+        }
+        double al = __shfl_up_sync(0xffffffffu, a.y, 1), ar = __shfl_down_sync(0xffffffffu, a.x, 1);
+        double bl = __shfl_up_sync(0xffffffffu, b.y, 1), br = __shfl_down_sync(0xffffffffu, b.x, 1);
+        if (lane == 0) {
+            al = cp > 0 ? (live ? r0[t - 1] : 0.0) : (prev0 ? __ldg(prev0 + i) : 0.0);
+            bl = cp > 0 ? (live ? r1[t - 1] : 0.0) : (prev1 ? __ldg(prev1 + i) : 0.0);
+        }
+        if (t + 2 == n) {
+            ar = next0 ? __ldg(next0 + i) : 0.0;
+            br = next1 ? __ldg(next1 + i) : 0.0;
+        } else if (lane == 31) {
+            ar = (t + 2 < n) ? r0[t + 2] : 0.0;
+            br = (t + 2 < n) ? r1[t + 2] : 0.0;
+        }
+        if (!live) continue;
+        double2 o1, o2;
+        o1.x = fma(c[5].x, b.y, fma(c[4].x, b.x, fma(c[3].x, bl,
+               fma(c[2].x, a.y, fma(c[1].x, a.x, c[0].x * al)))));
+        o1.y = fma(c[5].y, br, fma(c[4].y, b.y, fma(c[3].y, b.x,
+               fma(c[2].y, ar, fma(c[1].y, a.y, c[0].y * a.x)))));
+        o2.x = fma(c[11].x, b.y, fma(c[10].x, b.x, fma(c[9].x, bl,
+               fma(c[8].x, a.y, fma(c[7].x, a.x, c[6].x * al)))));
+        o2.y = fma(c[11].y, br, fma(c[10].y, b.y, fma(c[9].y, b.x,
+               fma(c[8].y, ar, fma(c[7].y, a.y, c[6].y * a.x)))));
+        stv2(y1 + (size_t)i * ldy + t, o1);
+        stv2(y2 + (size_t)i * ldy + t, o2);
+    }
+}
+
 // y0 = A0 x and y1 = A1 x for two matrices on one sparsity pattern: x and the
 // pattern are read once (M_x x and A_x x of heateq_mpi.py:166-178).
 __global__ void __launch_bounds__(256)
@@ -702,6 +767,33 @@ int stk_time_apply2(int M, int nrows_t, const int *indptr, const int *indices,
             M, nrows_t, indptr, indices, vals, x0, x1, ldx, ncols_local, xh0, n_halo0, xh1, alpha,
             beta, y, ldy, wy);
     return check_launch("k_time_apply2");
+}
+
+int stk_time_tridiag_pair(int M, int n, int ld, const double *coef, const double *x0,
+                          const double *x1, int ldx, const double *prev0, const double *next0,
+                          const double *prev1, const double *next1, double *y1, double *y2,
+                          int ldy, void *stream) {
+    if ((ld & 1) || (ldx & 1) || (ldy & 1) || n > ld || ld > ldx || ld > 2048)
+        return fail(-1, "stk_time_tridiag_pair: need even pitches, n <= ld <= ldx, ld <= 2048");
+    if (x0 == y1 || x0 == y2 || x1 == y1 || x1 == y2 || y1 == y2)
+        return fail(-1, "stk_time_tridiag_pair: aliasing");
+    if (M == 0 || ld == 0) return 0;
+    const int ld2 = ld / 2;
+    const int threads = (ld2 + 31) / 32 * 32;
+    int per_sm = 65536 / (threads * 88);  // ~82 registers per thread
+    if (per_sm > 8) per_sm = 8;
+    if (per_sm < 1) per_sm = 1;
+    int64_t grid = (int64_t)sm_count() * per_sm;
+    if (grid > M) grid = M;
+    cudaStream_t s = as_stream(stream);
+#define STK_TTP(NT)                                                                         \
+    k_time_tridiag_pair<NT><<<(unsigned)grid, threads, 0, s>>>(M, n, ld2, coef, ld, x0, x1, ldx, \
+                                                              prev0, next0, prev1, next1, y1, y2, ldy)
+    if (threads <= 256) STK_TTP(256);
+    else if (threads <= 512) STK_TTP(512);
+    else STK_TTP(1024);  // 64 registers per thread: a few coefficients spill
+#undef STK_TTP
+    return check_launch("k_time_tridiag_pair");
 }
 
 int stk_space_spmm_split(int nrows, const int *indptr, const int *indices, const double *vals0,

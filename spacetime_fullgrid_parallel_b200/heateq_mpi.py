@@ -68,6 +68,31 @@ class SchurOperatorMPI(LinearOperatorMPI):
         # all four tridiagonal stencils move the same +-1 slices
         assert len({plans[k]._key for k in ('A', 'L', 'LT', 'M')}) == 1
         self.overlap = os.environ.get('STK_OVERLAP', '1') != '0'
+        # both brackets in one pass when the four time matrices are
+        # tridiagonal (they are: heateq_mpi.py:78-88); else the general path
+        self._tri = None
+        mats = [sp.csr_matrix(T) for T in (A_t, L_t, L_t.T, M_t)]
+        if (os.environ.get('STK_TRIDIAG_PAIR', '1') != '0' and all(
+                abs(m.tocoo().row - m.tocoo().col).max(initial=0) <= 1
+                for m in mats)):
+            self._tri = mats
+
+    def _tridiag_coef(self, ld, device):
+        """coef[12][ld] of stk_time_tridiag_pair for this rank's rows."""
+        import numpy as np
+        d = self.dofs_distr
+        a, n, N = d.t_begin, d.t_end - d.t_begin, d.N
+        coef = np.zeros((12, ld))
+        for k, T in enumerate(self._tri):
+            for off in (-1, 0, 1):
+                rows = np.arange(a, a + n)
+                cols = rows + off
+                ok = (cols >= 0) & (cols < N)
+                vals = np.zeros(n)
+                vals[ok] = np.asarray(T[rows[ok], cols[ok]]).ravel()
+                coef[3 * k + off + 1, :n] = vals
+        # rows of coef: [Ta sub, dia, sup, Tb ..., Tc ..., Td ...]
+        return torch.from_numpy(coef).to(device)
 
     def _matvec(self, vec_in, vec_out):
         assert vec_in is not vec_out
@@ -94,9 +119,12 @@ class SchurOperatorMPI(LinearOperatorMPI):
                         device=vec_in.data.device)
         z = torch.empty_like(y)
         vec_out._invalidate()
-        self.bracket1.apply(mx, ax, y.data_ptr(), ldy=2 * ld)  # A_t Mx + L_t Ax
-        self.bracket2.apply(mx, ax, y.data_ptr() + 8 * ld,
-                            ldy=2 * ld)  # L_t^T Mx + M_t Ax
+        if self._tri is not None and ld <= 2048:
+            self._brackets_tridiag(mx, ax, y, ld)
+        else:
+            self.bracket1.apply(mx, ax, y.data_ptr(), ldy=2 * ld)  # A_t Mx + L_t Ax
+            self.bracket2.apply(mx, ax, y.data_ptr() + 8 * ld,
+                                ldy=2 * ld)  # L_t^T Mx + M_t Ax
         self.K.apply_block(y, z)
         self.MA.pair(z.data_ptr(), z.data_ptr() + 8 * ld, vec_out.data,
                      ldx=2 * ld)  # M z1 + A z2
@@ -105,6 +133,41 @@ class SchurOperatorMPI(LinearOperatorMPI):
             getattr(p, 'time_communication', 0.0)
             for p in self.plans.values()) - c0
         return vec_out
+
+
+def _brackets_tridiag(self, mx, ax, y, ld):
+    """y[:, :ld] = A_t Mx + L_t Ax and y[:, ld:] = L_t^T Mx + M_t Ax in one
+    pass over Mx and Ax (stk_time_tridiag_pair)."""
+    from ._lib import check, lib, ptr, stream
+    dev = mx.data.device
+    key = (ld, dev)
+    if getattr(self, '_tri_coef_key', None) != key:
+        self._tri_coef = self._tridiag_coef(ld, dev)
+        self._tri_coef_key = key
+    pl = self.plans['A']
+    hm = pl.fetch(mx) if pl.n_halo else None
+    ha = pl.fetch(ax) if pl.n_halo else None
+    d = self.dofs_distr
+    M = mx.M
+    has_prev, has_next = d.t_begin > 0, d.t_end < d.N
+
+    def slices(h):  # halo rows are sorted by global index: previous, then next
+        if h is None:
+            return None, None
+        prev = h.data_ptr() if has_prev else None
+        nxt = h.data_ptr() + 8 * M * (1 if has_prev else 0) if has_next else None
+        return prev, nxt
+
+    p0, n0 = slices(hm)
+    p1, n1 = slices(ha)
+    check(lib().stk_time_tridiag_pair(M, d.t_end - d.t_begin, ld,
+                                      ptr(self._tri_coef), ptr(mx.data),
+                                      ptr(ax.data), mx.ld, p0, n0, p1, n1,
+                                      y.data_ptr(), y.data_ptr() + 8 * ld,
+                                      2 * ld, stream()))
+
+
+SchurOperatorMPI._brackets_tridiag = _brackets_tridiag
 
 
 class HeatEquationMPI:

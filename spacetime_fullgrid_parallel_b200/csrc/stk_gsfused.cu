@@ -29,6 +29,7 @@ constexpr int GS_LOOKAHEAD = 2;  // must equal gs_program.LOOKAHEAD
 constexpr int GS_RING = 8;       // pass slots of the record ring (>= 2 * GS_MAXPASS + 2)
 constexpr int GS_FRING = 4;      // passes between requesting an op's f and using it (= gs_program.PREFETCH)
 constexpr int GS_MAXPASS = 3;    // passes per macro-step the host may emit (gs_program.MAX_PASSES)
+static_assert(GS_RING >= 2 * GS_MAXPASS + 2, "record ring too small for the passes of two steps");
 
 struct GsArgs {
     const int *item_step, *item_pass;

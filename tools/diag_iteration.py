@@ -75,8 +75,12 @@ def main():
         def s_brackets():
             st['y'] = torch.empty((heq.M, 2 * ld), dtype=torch.float64, device='cuda')
             st['z'] = torch.empty_like(st['y'])
-            S.bracket1.apply(st['mx'], st['ax'], st['y'].data_ptr(), ldy=2 * ld)
-            S.bracket2.apply(st['mx'], st['ax'], st['y'].data_ptr() + 8 * ld, ldy=2 * ld)
+            if getattr(S, '_tri', None) is not None and ld <= 2048:
+                S._brackets_tridiag(st['mx'], st['ax'], st['y'], ld)
+            else:
+                S.bracket1.apply(st['mx'], st['ax'], st['y'].data_ptr(), ldy=2 * ld)
+                S.bracket2.apply(st['mx'], st['ax'], st['y'].data_ptr() + 8 * ld,
+                                 ldy=2 * ld)
 
         phase('S: M x, A x (+ halo of x in flight)', s_split)
         phase('S: time stencils (2 brackets)', s_brackets)

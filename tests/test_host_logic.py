@@ -348,3 +348,36 @@ def test_locality_order_is_a_local_walk():
     index = np.abs(rows - A.indices).max()
     assert walk <= 2 * int(np.sqrt(n)) and index > 10 * walk
     assert locality_order(prob.hierarchy.P_mats[-1]) is None  # not square
+
+
+def test_tridiag_pair_coefficients():
+    """Coefficient table of stk_time_tridiag_pair (both brackets of the Schur
+    operator, heateq_mpi.py:166-178) for whole time axes and for slabs: applied
+    to [previous | local | next] slices it reproduces the local rows of
+    A_t X0 + L_t X1 and L_t^T X0 + M_t X1; pads and missing neighbours carry
+    zero coefficients."""
+    import types
+    from spacetime_fullgrid_parallel_b200.heateq_mpi import SchurOperatorMPI
+    prob = SquareProblem(1, 4)
+    N = prob.N
+    mats = [sp.csr_matrix(T) for T in (prob.A_t, prob.L_t, prob.L_t.T, prob.M_t)]
+    X0, X1 = rand((N, ), seed=1), rand((N, ), seed=2)
+    for a, b in ((0, N), (0, 8), (8, N), (5, 6)):
+        n = b - a
+        ld = max(4, (n + 3) // 4 * 4)
+        stub = types.SimpleNamespace(
+            dofs_distr=types.SimpleNamespace(t_begin=a, t_end=b, N=N), _tri=mats)
+        c = SchurOperatorMPI._tridiag_coef(stub, ld, 'cpu').numpy()
+        assert c.shape == (12, ld) and not c[:, n:].any()
+        if a == 0:
+            assert not c[0::3, 0].any()  # no previous slice: no sub-diagonal
+        if b == N:
+            assert not c[2::3, n - 1].any()
+        ext = [np.concatenate([[X[a - 1] if a > 0 else 0.0], X[a:b],
+                               [X[b] if b < N else 0.0]]) for X in (X0, X1)]
+        t = np.arange(n)
+        for k, ref in ((0, (mats[0] @ X0 + mats[1] @ X1)[a:b]),
+                       (6, (mats[2] @ X0 + mats[3] @ X1)[a:b])):
+            y = sum(c[k + 3 * v + o, :n] * ext[v][t + o]
+                    for v in (0, 1) for o in (0, 1, 2))
+            assert np.abs(y - ref).max() < 1e-14
